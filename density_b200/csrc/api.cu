@@ -1,0 +1,346 @@
+// api.cu — the C ABI of libdensity_b200.so (see include/density_b200.h).
+//
+// Entry points mirror the reference's extern "C" exports
+//   /root/reference/src/algorithms/chameleon/chameleon.rs:70-83
+//   /root/reference/src/algorithms/cheetah/cheetah.rs:105-118
+//   /root/reference/src/algorithms/lion/lion.rs:193-206
+// and add stream-ordered device-pointer variants. There is no CPU fallback anywhere in this file: if CUDA is
+// unavailable every call fails with DENSITY_B200_ECUDA / returns 0.
+#include "../../include/density_b200.h"
+#include "common.cuh"
+#include "encode_internal.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+namespace dns {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static void set_error(const char* what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    g_last_error = buf;
+}
+static void set_error(const char* what) { g_last_error = what; }
+
+// grow-only device buffer
+struct DevBuf {
+    uint8_t* p = nullptr; size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        size_t want = need + need / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, need); want = need; }
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct DeviceCtx {
+    int dev = -1;
+    int num_sms = 0;
+    bool ready = false;
+    cudaStream_t stream = nullptr;     // for the synchronous host-pointer entry points
+    DevBuf ws, stage_in, stage_out;
+    uint64_t* d_size = nullptr;        // 8 B device
+    uint64_t* h_size = nullptr;        // 8 B pinned
+    ChamLayout layout{};
+    int last_was_chameleon_fastpath_capable = 0;
+    std::mutex mu;
+};
+
+constexpr int MAX_DEVICES = 64;
+static DeviceCtx g_ctx[MAX_DEVICES];
+static std::mutex g_ctx_mu;
+
+static DeviceCtx* current_ctx() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("cudaGetDevice", e); return nullptr; }
+    if (dev < 0 || dev >= MAX_DEVICES) { set_error("device index out of range"); return nullptr; }
+    DeviceCtx* c = &g_ctx[dev];
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!c->ready) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) { set_error("cudaGetDeviceProperties", e); return nullptr; }
+        if (prop.major < 10) { set_error("density_b200 requires an sm_100a device (B200)"); return nullptr; }
+        c->dev = dev;
+        c->num_sms = prop.multiProcessorCount;
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { set_error("cudaStreamCreate", e); return nullptr; }
+        e = cudaMalloc(&c->d_size, 64);
+        if (e != cudaSuccess) { set_error("cudaMalloc", e); return nullptr; }
+        e = cudaMallocHost(&c->h_size, 64);
+        if (e != cudaSuccess) { set_error("cudaMallocHost", e); return nullptr; }
+        c->ready = true;
+    }
+    return c;
+}
+
+static size_t safe_size(int alg, size_t size) {  // codec/codec.rs:18-21
+    const size_t B = alg_block_bytes(alg), S = alg_sig_bytes(alg);
+    return size + (size / B) * S + ((size % B) ? S : 0);
+}
+
+static bool is_device_pointer(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// path: 0 auto (fast path with exact fallback), 1 fast only (no fallback), 2 protected walk only, 3 scalar kernel
+static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                uint64_t* d_out_size, cudaStream_t stream, int path) {
+    uint64_t launches = 0;
+    cudaError_t e;
+    if (alg == ALG_CHAMELEON && path != 3) {
+        if ((reinterpret_cast<uintptr_t>(d_in) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 1)) { set_error("encode_device: d_in must be 4-byte and d_out 2-byte aligned"); return DENSITY_B200_EARG; }
+        ChamLayout L;
+        size_t need = cham_workspace_bytes(n, c->num_sms, &L);
+        e = c->ws.ensure(need);
+        if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+        c->layout = L;
+        if (path == 2) {
+            e = cham_encode_protected_only(d_in, n, c->ws.p, L, d_out, cap, d_out_size, stream, &launches);
+        } else {
+            const uint32_t nruns = cham_pick_runs(n, c->num_sms);
+            e = cham_encode_phase1(d_in, n, c->ws.p, L, nruns, nullptr, stream, &launches);
+            if (e == cudaSuccess)
+                e = cham_encode_phase2(d_in, n, c->ws.p, L, nruns, nullptr, d_out, cap, d_out_size, path == 0, false, stream, &launches);
+        }
+        c->last_was_chameleon_fastpath_capable = (path != 2);
+    } else {
+        if (reinterpret_cast<uintptr_t>(d_out) & 1) { set_error("encode_device: d_out must be 2-byte aligned"); return DENSITY_B200_EARG; }
+        e = c->ws.ensure(scalar_workspace_bytes(alg));
+        if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+        e = scalar_encode(alg, d_in, n, d_out, cap, c->ws.p, d_out_size, stream, &launches);
+        c->last_was_chameleon_fastpath_capable = 0;
+    }
+    g_launches += launches;
+    if (e != cudaSuccess) { set_error("encode launch", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+
+static int decode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                uint64_t* d_out_size, cudaStream_t stream) {
+    uint64_t launches = 0;
+    cudaError_t e = c->ws.ensure(scalar_workspace_bytes(alg));
+    if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+    e = scalar_decode(alg, d_in, n, d_out, cap, c->ws.p, d_out_size, stream, &launches);
+    g_launches += launches;
+    if (e != cudaSuccess) { set_error("decode launch", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+
+// Synchronous entry point shared by the nine reference-shaped symbols.
+static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap) {
+    g_last_error.clear();
+    if ((!in && n) || (!out && out_cap)) { set_error("null pointer"); return 0; }
+    if (n == 0) return 0;  // Codec::encode/decode of an empty slice writes nothing (codec.rs:76,102)
+    DeviceCtx* c = current_ctx();
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
+    cudaError_t e;
+    const uint8_t* d_in = in;
+    uint8_t* d_out = out;
+    size_t d_cap = out_cap;
+    if (!in_dev) {
+        e = c->stage_in.ensure(n + 16);
+        if (e != cudaSuccess) { set_error("staging cudaMalloc", e); return 0; }
+        e = cudaMemcpyAsync(c->stage_in.p, in, n, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { set_error("H2D copy", e); return 0; }
+        d_in = c->stage_in.p;
+    }
+    if (!out_dev) {
+        // encode: stage into a full safe-size buffer and check the real size against the caller's capacity afterwards
+        // (the reference only fails when the bytes actually written exceed the slice, write_buffer.rs:19)
+        d_cap = encode ? safe_size(alg, n) : out_cap;
+        e = c->stage_out.ensure(d_cap + 16);
+        if (e != cudaSuccess) { set_error("staging cudaMalloc", e); return 0; }
+        d_out = c->stage_out.p;
+    }
+    int rc = encode ? encode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream, 0)
+                    : decode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream);
+    if (rc != DENSITY_B200_OK) { cudaStreamSynchronize(c->stream); return 0; }
+    e = cudaMemcpyAsync(c->h_size, c->d_size, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_error("stream sync", e); return 0; }
+    const uint64_t produced = *c->h_size;
+    if (produced == 0) { set_error(encode ? "encode failed on device (output capacity?)" : "decode failed on device (malformed stream or output capacity)"); return 0; }
+    if (produced > out_cap) { set_error("output buffer too small"); return 0; }
+    if (!out_dev) {
+        e = cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error("D2H copy", e); return 0; }
+    }
+    return (size_t)produced;
+}
+
+}  // namespace dns
+
+using namespace dns;
+
+extern "C" {
+
+size_t chameleon_encode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(true, ALG_CHAMELEON, i, n, o, c); }
+size_t chameleon_decode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(false, ALG_CHAMELEON, i, n, o, c); }
+size_t chameleon_safe_encode_buffer_size(size_t s) { return safe_size(ALG_CHAMELEON, s); }
+size_t cheetah_encode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(true, ALG_CHEETAH, i, n, o, c); }
+size_t cheetah_decode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(false, ALG_CHEETAH, i, n, o, c); }
+size_t cheetah_safe_encode_buffer_size(size_t s) { return safe_size(ALG_CHEETAH, s); }
+size_t lion_encode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(true, ALG_LION, i, n, o, c); }
+size_t lion_decode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(false, ALG_LION, i, n, o, c); }
+size_t lion_safe_encode_buffer_size(size_t s) { return safe_size(ALG_LION, s); }
+
+static int device_entry(bool encode, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                        void* stream, int path) {
+    g_last_error.clear();
+    if (alg < 0 || alg > 2) { set_error("bad algorithm id"); return DENSITY_B200_EARG; }
+    if (!d_out_size || (!d_in && n) || (!d_out && cap)) { set_error("null pointer"); return DENSITY_B200_EARG; }
+    DeviceCtx* c = current_ctx();
+    if (!c) return DENSITY_B200_ECUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(d_out_size, 0, sizeof(uint64_t), s);
+        if (e != cudaSuccess) { set_error("memset", e); return DENSITY_B200_ECUDA; }
+        return DENSITY_B200_OK;
+    }
+    return encode ? encode_device_locked(c, alg, d_in, n, d_out, cap, d_out_size, s, path)
+                  : decode_device_locked(c, alg, d_in, n, d_out, cap, d_out_size, s);
+}
+
+int density_b200_encode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size, void* stream) {
+    return device_entry(true, alg, d_in, n, d_out, cap, d_out_size, stream, 0);
+}
+int density_b200_decode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size, void* stream) {
+    return device_entry(false, alg, d_in, n, d_out, cap, d_out_size, stream, 0);
+}
+int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                                    void* stream, int path) {
+    if (path < 0 || path > 3) { set_error("bad path"); return DENSITY_B200_EARG; }
+    return device_entry(true, alg, d_in, n, d_out, cap, d_out_size, stream, path);
+}
+
+// ---- sharded Chameleon encode ------------------------------------------------------------------------
+struct density_b200_shard {
+    DevBuf ws;
+    ChamLayout L{};
+    const uint8_t* d_in = nullptr;
+    size_t n = 0;
+    uint32_t nruns = 0;
+    int is_last = 1;
+    int num_sms = 0;
+    bool phase1_done = false;
+};
+
+density_b200_shard* density_b200_shard_create(void) {
+    g_last_error.clear();
+    DeviceCtx* c = current_ctx();
+    if (!c) return nullptr;
+    density_b200_shard* s = new density_b200_shard();
+    s->num_sms = c->num_sms;
+    return s;
+}
+void density_b200_shard_destroy(density_b200_shard* s) {
+    if (!s) return;
+    s->ws.release();
+    delete s;
+}
+int density_b200_shard_phase1(density_b200_shard* s, const uint8_t* d_in, size_t n, int is_last_shard, uint32_t* d_table_out, void* stream) {
+    g_last_error.clear();
+    if (!s || (!d_in && n) || !d_table_out) { set_error("null pointer"); return DENSITY_B200_EARG; }
+    if (!is_last_shard && (n % 256)) { set_error("non-final shards must be a multiple of 256 bytes"); return DENSITY_B200_EARG; }
+    if (reinterpret_cast<uintptr_t>(d_in) & 3) { set_error("d_in must be 4-byte aligned"); return DENSITY_B200_EARG; }
+    size_t need = cham_workspace_bytes(n, s->num_sms, &s->L);
+    cudaError_t e = s->ws.ensure(need);
+    if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+    s->d_in = d_in; s->n = n; s->is_last = is_last_shard; s->nruns = cham_pick_runs(n, s->num_sms);
+    uint64_t launches = 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        e = cudaMemsetAsync(d_table_out, 0, 65536 * sizeof(uint32_t), st);  // nothing touched
+    } else {
+        e = cham_encode_phase1(d_in, n, s->ws.p, s->L, s->nruns, d_table_out, st, &launches);
+    }
+    g_launches += launches;
+    if (e != cudaSuccess) { set_error("shard phase1", e); return DENSITY_B200_ECUDA; }
+    s->phase1_done = true;
+    return DENSITY_B200_OK;
+}
+int density_b200_shard_phase2(density_b200_shard* s, const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                              uint32_t* d_flags, void* stream) {
+    g_last_error.clear();
+    if (!s || !s->phase1_done || !d_out_size) { set_error("shard_phase2: phase1 not done / null pointer"); return DENSITY_B200_EARG; }
+    if (reinterpret_cast<uintptr_t>(d_out) & 1) { set_error("d_out must be 2-byte aligned"); return DENSITY_B200_EARG; }
+    uint64_t launches = 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cham_encode_phase2(s->d_in, s->n, s->ws.p, s->L, s->nruns, d_carry_in, d_out, cap, d_out_size, false,
+                                       d_carry_in != nullptr, st, &launches);
+    if (e == cudaSuccess && d_flags) {
+        if (s->n) e = cudaMemcpyAsync(d_flags, s->ws.p + s->L.status + offsetof(Status, nonquiet), sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+        else e = cudaMemsetAsync(d_flags, 0, sizeof(uint32_t), st);
+    }
+    g_launches += launches;
+    if (e != cudaSuccess) { set_error("shard phase2", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+int density_b200_table_init(uint32_t* d_table, void* stream) {
+    uint64_t l = 0;
+    cudaError_t e = cham_table_init(d_table, reinterpret_cast<cudaStream_t>(stream), &l);
+    g_launches += l;
+    if (e != cudaSuccess) { set_error("table_init", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+int density_b200_table_fold(uint32_t* d_acc, const uint32_t* d_next, void* stream) {
+    uint64_t l = 0;
+    cudaError_t e = cham_table_fold(d_acc, d_next, reinterpret_cast<cudaStream_t>(stream), &l);
+    g_launches += l;
+    if (e != cudaSuccess) { set_error("table_fold", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+
+// ---- housekeeping ----------------------------------------------------------------------------------------
+const char* density_b200_last_error(void) { return g_last_error.c_str(); }
+uint64_t density_b200_kernel_launches(void) { return g_launches.load(); }
+
+int density_b200_last_encode_was_fast(void) {
+    DeviceCtx* c = current_ctx();
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->last_was_chameleon_fastpath_capable || !c->ws.p) return 0;
+    Status st;
+    if (cudaMemcpy(&st, c->ws.p + c->layout.status, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return st.nonquiet ? 0 : 1;
+}
+
+void density_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        DeviceCtx& c = g_ctx[d];
+        if (!c.ready) continue;
+        cudaSetDevice(d);
+        c.ws.release(); c.stage_in.release(); c.stage_out.release();
+        if (c.d_size) cudaFree(c.d_size);
+        if (c.h_size) cudaFreeHost(c.h_size);
+        if (c.stream) cudaStreamDestroy(c.stream);
+        c.d_size = nullptr; c.h_size = nullptr; c.stream = nullptr; c.ready = false;
+    }
+    if (cur >= 0) cudaSetDevice(cur);
+}
+
+const char* density_b200_version(void) { return "density_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,777 @@
+// chameleon_encode.cu — Chameleon encode for sm_100a.
+//
+// Replaces /root/reference/src/algorithms/chameleon/chameleon.rs:86-101 (encode_quad) driven by
+// /root/reference/src/codec/codec.rs:34-80 (encode_block / encode), bit-exactly.
+//
+// The reference walks the stream once with ONE 65,536-entry dictionary that every quad reads and (on a
+// miss) writes, so flag i depends on the most recent earlier quad with the same 16-bit hash. This file
+// turns that into a data-parallel computation:
+//
+//   flag_i = 1  <=>  the previous quad in the same hash bucket (in stream order, skipping copy-mode blocks)
+//                    equals quad_i; an empty bucket behaves as "holds quad 0".
+//
+// Pass 1  cham_flag_pass      one persistent CTA per SM; CTA r owns the contiguous run r of the stream and
+//                             keeps the run's dictionary in shared memory as 16-bit fingerprints (128 KiB,
+//                             see common.cuh). It walks the run in tiles of 4096 quads; inside a tile the
+//                             "previous in bucket" relation is resolved with a barrier-phased optimistic
+//                             protocol (A read / B racy publish / C read back / D classify) and a small
+//                             in-order slow path for buckets that really interleave different values.
+//                             First touches of a bucket inside a run cannot know the dictionary carried in
+//                             from earlier runs; they are recorded in an "unresolved" list.
+//         cham_carry_scan     per-bucket left fold of the runs' last-writer tables -> carry-in table per run.
+//         cham_resolve        patches the unresolved flags from the carry-in tables.
+//         cham_tile_sizes     per-block output sizes -> per-tile byte counts; detects whether the reference's
+//                             protection automaton (codec/protection_state.rs) could ever have fired.
+//         scan kernels        exclusive scan of the tile byte counts.
+// Pass 2  cham_emit           re-reads the input, writes signatures + 2/4-byte payload at the scanned offsets.
+//
+// If two consecutive blocks are incompressible the automaton may switch to copy mode, which removes blocks
+// from the dictionary history. That case is handled by cham_protected_pass: an exact, in-order,
+// protection-aware single-CTA walk (also the device-side checker for the fast path in the tests).
+#include "common.cuh"
+#include "encode_internal.cuh"
+
+namespace dns {
+namespace cham {
+
+// ------------------------------------------------------------------------------------------------------
+// Pass 1: flag pass
+// ------------------------------------------------------------------------------------------------------
+constexpr int FP_THREADS = 1024;
+constexpr int FP_WARPS = FP_THREADS / 32;
+constexpr int FP_QPT = 4;                          // quads per thread per tile
+constexpr int TILE_Q = FP_THREADS * FP_QPT;        // 4096 quads = 16 KiB = 64 blocks
+constexpr int SIDE_N = 8192;                       // first-misser table (u32), indexed by hash & (SIDE_N-1)
+constexpr uint32_t SIDE_EMPTY = 0xFFFFFFFFu;
+
+struct FlagSmem {
+    uint16_t tab[65536];          // fingerprint of the last quad seen in each bucket
+    uint32_t vbit[2048];          // "bucket touched" for the one case tab cannot express (fingerprint 0)
+    uint32_t conf[2048];          // per-tile conflict bits (bucket interleaves different values)
+    uint32_t side[SIDE_N];        // per-tile min over missers of (pos << 16 | hash)
+    uint2 slowdata[TILE_Q];       // published by slow members: {hash | fp << 16, old | touched << 16}
+    uint16_t slowlist[TILE_Q];    // positions of slow members, ascending
+    uint32_t slowmap[TILE_Q / 32];
+    uint32_t sigw[TILE_Q / 32];   // flag bits of the tile: word (w*4+j) = ballot of warp w, sub-row j
+    uint32_t unres_count;
+};
+static_assert(sizeof(FlagSmem) <= 227 * 1024, "flag pass shared memory");
+
+// status bits kept per quad in a register
+enum : uint32_t { ST_ACTIVE = 1, ST_TOUCHED = 2, ST_MISS = 4, ST_SLOW = 8, ST_FLAG = 16, ST_UNRES = 32, ST_SETTER = 64, ST_FIRST = 128, ST_TENT = 256 };
+
+__device__ __forceinline__ bool bit_test(const uint32_t* bm, uint32_t i) { return (bm[i >> 5] >> (i & 31)) & 1u; }
+
+// Append the lanes with `pred` set to the run's unresolved list (warp-aggregated).
+__device__ __forceinline__ void append_unres(bool pred, uint32_t qidx_in_run, uint32_t h, uint32_t f,
+                                             uint32_t* s_count, uint2* __restrict__ unres_run) {
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (m == 0) return;
+    uint32_t base = 0;
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane == 0) base = atomicAdd(s_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (pred) {
+        uint32_t idx = base + __popc(m & lanemask_lt());
+        if (idx < 65536u) unres_run[idx] = make_uint2(qidx_in_run, h | (f << 16));
+    }
+}
+
+__global__ void __launch_bounds__(FP_THREADS, 1)
+cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_total, uint32_t nruns,
+               uint32_t* __restrict__ sigw_g,        // 2 x u32 per block (low half first)
+               uint2* __restrict__ unres,            // nruns x 65536
+               uint32_t* __restrict__ unres_count,   // nruns
+               uint32_t* __restrict__ final_tab)     // nruns x 65536: touched << 16 | fp
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FlagSmem& S = *reinterpret_cast<FlagSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t run = blockIdx.x;
+    const uint64_t t_begin = (uint64_t)run * tiles_total / nruns;
+    const uint64_t t_end = (uint64_t)(run + 1) * tiles_total / nruns;
+    uint2* __restrict__ unres_run = unres + (size_t)run * 65536;
+
+    // ---- init shared state -------------------------------------------------------------------------
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* t4 = reinterpret_cast<uint4*>(S.tab);
+        for (uint32_t i = tid; i < 65536 * 2 / 16; i += FP_THREADS) t4[i] = z;
+        for (uint32_t i = tid; i < 2048; i += FP_THREADS) { S.vbit[i] = 0; S.conf[i] = 0; }
+        for (uint32_t i = tid; i < SIDE_N; i += FP_THREADS) S.side[i] = SIDE_EMPTY;
+        if (tid == 0) S.unres_count = 0;
+    }
+    __syncthreads();
+
+    // ---- prefetch the first tile --------------------------------------------------------------------
+    uint32_t nxt[FP_QPT];
+#pragma unroll
+    for (int j = 0; j < FP_QPT; ++j) {
+        uint64_t gi = t_begin * TILE_Q + warp * 128 + j * 32 + lane;
+        nxt[j] = (t_begin < t_end && gi < nquads) ? ld_stream_u32(in + gi) : 0u;
+    }
+
+    for (uint64_t t = t_begin; t < t_end; ++t) {
+        uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT], old[FP_QPT], st[FP_QPT];
+        const uint64_t tile_q0 = t * TILE_Q;
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            q[j] = nxt[j];
+            uint64_t gi = tile_q0 + warp * 128 + j * 32 + lane;
+            st[j] = (gi < nquads) ? ST_ACTIVE : 0u;
+        }
+        // prefetch next tile (register double buffer; consumed one full tile later)
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            uint64_t gi = (t + 1) * TILE_Q + warp * 128 + j * 32 + lane;
+            nxt[j] = (t + 1 < t_end && gi < nquads) ? ld_stream_u32(in + gi) : 0u;
+        }
+
+        // ---- phase A: read the pre-tile dictionary --------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            uint32_t p = hash_prod(q[j]);
+            h[j] = prod_hash(p);
+            f[j] = prod_fp(p, q[j]);
+            old[j] = S.tab[h[j]];
+        }
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            bool touched = old[j] != 0;
+            if (!touched) touched = bit_test(S.vbit, h[j]);
+            if (touched) st[j] |= ST_TOUCHED;
+            bool hit = touched && old[j] == f[j];
+            if ((st[j] & ST_ACTIVE) && !hit) st[j] |= ST_MISS;
+        }
+        __syncthreads();  // S1: all reads of tab/vbit precede the publishes
+
+        // ---- phase B: missers publish ---------------------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            if (st[j] & ST_MISS) {
+                S.tab[h[j]] = (uint16_t)f[j];  // racy between different values on purpose
+                uint32_t pos = warp * 128 + j * 32 + lane;
+                atomicMin(&S.side[h[j] & (SIDE_N - 1)], (pos << 16) | h[j]);
+            }
+        }
+        __syncthreads();  // S2
+
+        // ---- phase C: read back, raise conflict bits ------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            if (!(st[j] & ST_ACTIVE)) continue;
+            const uint32_t pos = warp * 128 + j * 32 + lane;
+            const uint32_t w = S.tab[h[j]];
+            if (!(st[j] & ST_MISS)) {
+                // hit member: the bucket still holds my value unless some misser published (its value != mine)
+                if (w == f[j]) {
+                    st[j] |= ST_FLAG;
+                } else {
+                    uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
+                    if ((slot & 0xFFFFu) == h[j] && pos < (slot >> 16)) st[j] |= ST_FLAG;  // every misser of my bucket comes after me
+                    else st[j] |= ST_SLOW | ST_SETTER;
+                }
+            } else {
+                uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
+                if ((slot & 0xFFFFu) != h[j] || w != f[j]) st[j] |= ST_SLOW | ST_SETTER;  // foreign slot owner, or missers disagree
+                else {
+                    st[j] |= ST_TENT;
+                    if (slot == ((pos << 16) | h[j])) st[j] |= ST_FIRST;
+                }
+            }
+            if (st[j] & ST_SETTER) atomicOr(&S.conf[h[j] >> 5], 1u << (h[j] & 31));
+        }
+        __syncthreads();  // S3
+
+        // ---- phase D: classify, publish slow members, restore their buckets --------------------------
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            const uint32_t pos = warp * 128 + j * 32 + lane;
+            if (st[j] & ST_TENT) {
+                if (bit_test(S.conf, h[j])) {
+                    st[j] |= ST_SLOW;
+                } else if (st[j] & ST_FIRST) {
+                    // first misser of a bucket whose missers all agree: a genuine miss (or unresolved first touch)
+                    if (!(st[j] & ST_TOUCHED)) st[j] |= ST_UNRES;
+                    if (f[j] == 0) atomicOr(&S.vbit[h[j] >> 5], 1u << (h[j] & 31));
+                } else {
+                    st[j] |= ST_FLAG;  // predecessor in the bucket is a misser with my value
+                }
+            }
+            if (st[j] & ST_MISS) S.side[h[j] & (SIDE_N - 1)] = SIDE_EMPTY;
+            if (st[j] & ST_SLOW) {
+                S.slowdata[pos] = make_uint2(h[j] | (f[j] << 16), old[j] | ((st[j] & ST_TOUCHED) ? 0x10000u : 0u));
+                S.tab[h[j]] = (uint16_t)old[j];  // every slow member of a bucket writes the same pre-tile value
+            }
+            uint32_t sb = __ballot_sync(0xFFFFFFFFu, (st[j] & ST_SLOW) != 0);
+            uint32_t fb = __ballot_sync(0xFFFFFFFFu, (st[j] & ST_FLAG) != 0);
+            if (lane == 0) { S.slowmap[warp * 4 + j] = sb; S.sigw[warp * 4 + j] = fb; }
+        }
+        __syncthreads();  // S4
+
+        // ---- phase F: unresolved appends, conflict-bit cleanup, slow path (warp 0) -------------------
+        const uint32_t run_q0 = (uint32_t)((t - t_begin) * TILE_Q);
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            append_unres((st[j] & ST_UNRES) != 0, run_q0 + warp * 128 + j * 32 + lane, h[j], f[j], &S.unres_count, unres_run);
+            if (st[j] & ST_SETTER) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
+        }
+        if (warp == 0) {
+            // position-sorted list of slow members from the bitmap
+            uint32_t w0 = S.slowmap[lane * 4 + 0], w1 = S.slowmap[lane * 4 + 1], w2 = S.slowmap[lane * 4 + 2], w3 = S.slowmap[lane * 4 + 3];
+            uint32_t cnt = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+            const uint32_t nslow = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (nslow) {
+                uint32_t o = incl - cnt;
+                uint32_t ws[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t m = ws[k];
+                    while (m) { uint32_t b = __ffs(m) - 1; m &= m - 1; S.slowlist[o++] = (uint16_t)((lane * 4 + k) * 32 + b); }
+                }
+                __syncwarp();
+                for (uint32_t c = 0; c < nslow; c += 32) {
+                    const uint32_t i = c + lane;
+                    const bool valid = i < nslow;
+                    uint32_t pos = 0, hh = 0x10000u + lane, ff = 0;
+                    if (valid) { pos = S.slowlist[i]; uint2 d = S.slowdata[pos]; hh = d.x & 0xFFFFu; ff = d.x >> 16; }
+                    uint32_t cur = 0; bool touched = false;
+                    if (valid) { cur = S.tab[hh]; touched = cur != 0 || bit_test(S.vbit, hh); }
+                    const uint32_t grp = __match_any_sync(0xFFFFFFFFu, hh);
+                    const uint32_t lower = grp & lanemask_lt();
+                    const int pl = lower ? 31 - __clz(lower) : 0;
+                    const uint32_t fprev = __shfl_sync(0xFFFFFFFFu, ff, pl);
+                    const bool hit = lower ? (fprev == ff) : (touched && cur == ff);
+                    const bool is_last = (grp & lanemask_gt()) == 0;
+                    const bool unres_here = valid && !lower && !touched;
+                    if (valid) {
+                        if (hit) atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));
+                        if (is_last && (lower || !hit)) {
+                            S.tab[hh] = (uint16_t)ff;
+                            if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                        }
+                    }
+                    append_unres(unres_here, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();  // S5: dictionary final for this tile, sigw final
+
+        if (tid < TILE_Q / 32) sigw_g[tile_q0 / 32 + tid] = S.sigw[tid];  // workspace is sized in whole tiles
+        // (next iteration's phase D rewrites S.sigw only after three more barriers)
+    }
+
+    // ---- export the run's last-writer table ---------------------------------------------------------
+    for (uint32_t i = tid; i < 65536; i += FP_THREADS) {
+        uint32_t v = S.tab[i];
+        uint32_t tch = (v != 0 || bit_test(S.vbit, i)) ? 0x10000u : 0u;
+        final_tab[(size_t)run * 65536 + i] = v | tch;
+    }
+    if (tid == 0) unres_count[run] = S.unres_count < 65536u ? S.unres_count : 65536u;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// carry-in tables: carry[r] = state of the dictionary before run r (as touched<<16 | fp)
+// `init` = state before run 0 (NULL: the stream start, where only bucket 0 "holds quad 0").
+// ------------------------------------------------------------------------------------------------------
+__global__ void cham_carry_scan(const uint32_t* __restrict__ final_tab, const uint32_t* __restrict__ init, int init_untouched,
+                                uint32_t nruns, uint32_t* __restrict__ carry, uint32_t* __restrict__ table_out) {
+    uint32_t hb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hb >= 65536) return;
+    uint32_t c = init ? init[hb] : ((hb == 0 && !init_untouched) ? 0x10000u : 0u);
+    for (uint32_t r = 0; r < nruns; ++r) {
+        if (carry) carry[(size_t)r * 65536 + hb] = c;
+        uint32_t v = final_tab[(size_t)r * 65536 + hb];
+        if (v & 0x10000u) c = v;
+    }
+    if (table_out) table_out[hb] = c;
+}
+
+__global__ void cham_resolve(const uint2* __restrict__ unres, const uint32_t* __restrict__ unres_count,
+                             const uint32_t* __restrict__ carry, uint32_t tiles_total, uint32_t nruns,
+                             uint32_t* __restrict__ sigw_g) {
+    const uint32_t run = blockIdx.y;
+    const uint32_t n = unres_count[run];
+    const uint64_t run_q0 = ((uint64_t)run * tiles_total / nruns) * TILE_Q;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint2 e = unres[(size_t)run * 65536 + i];
+        uint32_t c = carry[(size_t)run * 65536 + (e.y & 0xFFFFu)];
+        if ((c & 0x10000u) && (c & 0xFFFFu) == (e.y >> 16)) {
+            uint64_t gq = run_q0 + e.x;
+            atomicOr(&sigw_g[gq >> 5], 1u << (gq & 31));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Exact protection-aware walk (single CTA, one warp walks the blocks in order).
+// Handles every input; used when the fast path reports `nonquiet`, and as the device-side checker.
+// `start_state`: dictionary before the first block (NULL = stream start).
+// ------------------------------------------------------------------------------------------------------
+struct ProtSmem {
+    uint16_t tab[65536];
+    uint32_t vbit[2048];
+};
+
+__global__ void __launch_bounds__(1024, 1)
+cham_protected_pass(const uint32_t* __restrict__ in, uint64_t nbytes, const Status* __restrict__ status, int only_if_nonquiet,
+                    uint32_t* __restrict__ sigw_g, uint8_t* __restrict__ copymap) {
+    if (only_if_nonquiet && status->nonquiet == 0) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ProtSmem& S = *reinterpret_cast<ProtSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* t4 = reinterpret_cast<uint4*>(S.tab);
+        for (uint32_t i = tid; i < 65536 * 2 / 16; i += blockDim.x) t4[i] = z;
+        for (uint32_t i = tid; i < 2048; i += blockDim.x) S.vbit[i] = (i == 0) ? 1u : 0u;  // bucket 0 "holds quad 0"
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+
+    const uint64_t nquads = nbytes / 4;
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    Protection ps; ps.init();
+    // register double buffer of the block's 64 quads (2 per lane)
+    uint32_t n0 = 0, n1 = 0;
+    if (nblocks) {
+        if (lane < nquads) n0 = in[lane];
+        if (32 + lane < nquads) n1 = in[32 + lane];
+    }
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        const uint32_t q0 = n0, q1 = n1;
+        {
+            uint64_t g = (b + 1) * 64 + lane;
+            n0 = (b + 1 < nblocks && g < nquads) ? in[g] : 0u;
+            n1 = (b + 1 < nblocks && g + 32 < nquads) ? in[g + 32] : 0u;
+        }
+        const uint64_t bq0 = b * 64;
+        const uint32_t nq = (uint32_t)((nquads - bq0 < 64) ? (nquads - bq0) : 64);  // quads in this block (may be 0)
+        if (ps.revert_to_copy()) {
+            if (lane == 0) { copymap[b] = 1; sigw_g[2 * b] = 0; sigw_g[2 * b + 1] = 0; }
+            ps.decay();
+            continue;
+        }
+        uint32_t sig[2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t q = half ? q1 : q0;
+            const bool valid = half * 32 + lane < nq;
+            const uint32_t p = hash_prod(q);
+            uint32_t hh = valid ? prod_hash(p) : 0x10000u + lane;
+            const uint32_t ff = prod_fp(p, q);
+            uint32_t cur = 0; bool touched = false;
+            if (valid) { cur = S.tab[hh]; touched = cur != 0 || bit_test(S.vbit, hh); }
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, hh);
+            const uint32_t lower = grp & lanemask_lt();
+            const int pl = lower ? 31 - __clz(lower) : 0;
+            const uint32_t fprev = __shfl_sync(0xFFFFFFFFu, ff, pl);
+            const bool hit = valid && (lower ? (fprev == ff) : (touched && cur == ff));
+            const bool is_last = (grp & lanemask_gt()) == 0;
+            if (valid && is_last && (lower || !hit)) {
+                S.tab[hh] = (uint16_t)ff;
+                if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+            }
+            sig[half] = __ballot_sync(0xFFFFFFFFu, hit);
+            __syncwarp();
+        }
+        if (lane == 0) { copymap[b] = 0; sigw_g[2 * b] = sig[0]; sigw_g[2 * b + 1] = sig[1]; }
+        const uint32_t hits = __popc(sig[0]) + __popc(sig[1]);
+        const uint32_t tailb = (b == nblocks - 1) ? (uint32_t)(nbytes & 3) : 0u;
+        const uint32_t out_sz = 8 + 4 * nq - 2 * hits + tailb;
+        ps.update(out_sz >= 256);  // codec.rs:68
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-tile output sizes + quiet check. One warp per tile (64 blocks, 2 per lane).
+// ------------------------------------------------------------------------------------------------------
+// encoded block: 8-byte signature + 4 bytes per plain quad + 2 per mapped quad + 1..3 raw tail bytes (codec.rs:39-68);
+// copy-mode block: the raw bytes (codec.rs:36).
+__device__ __forceinline__ uint32_t block_out_bytes(uint64_t b, uint64_t nbytes, uint32_t hits, bool copied) {
+    const uint64_t boff = b * 256;
+    const uint32_t blen = (uint32_t)((nbytes - boff < 256) ? (nbytes - boff) : 256);
+    return copied ? blen : 8 + blen - 2 * hits;
+}
+
+__global__ void cham_tile_sizes(const uint32_t* __restrict__ sigw_g, const uint8_t* __restrict__ copymap, uint64_t nbytes,
+                                uint64_t nblocks, uint32_t ntiles, int use_copymap_if_nonquiet, int check_quiet, int assume_prev_inc,
+                                Status* __restrict__ status, uint32_t* __restrict__ tile_bytes) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    const bool use_cm = copymap && (!use_copymap_if_nonquiet || status->nonquiet);
+    uint32_t sum = 0, incm[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint64_t b = (uint64_t)tile * 64 + k * 32 + lane;
+        uint32_t sz = 0; bool inc = false;
+        if (b < nblocks) {
+            const bool copied = use_cm && copymap[b];
+            const uint32_t hits = __popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]);
+            sz = block_out_bytes(b, nbytes, hits, copied);
+            inc = !copied && sz >= 256 && (nbytes - b * 256 >= 256);
+        }
+        sum += sz;
+        incm[k] = __ballot_sync(0xFFFFFFFFu, inc);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0) tile_bytes[tile] = sum;
+    if (check_quiet && lane == 0) {
+        // adjacent incompressible pair anywhere => the automaton's copy_penalty would become non-zero
+        bool prev = assume_prev_inc != 0;  // shard seam: the previous shard's last block is unknown here
+        if (tile > 0) {
+            const uint64_t b = (uint64_t)tile * 64 - 1;
+            const uint32_t hits = __popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]);
+            prev = (8 + 256 - 2 * hits) >= 256;
+        }
+        const uint64_t m = ((uint64_t)incm[1] << 32) | incm[0];
+        const uint64_t pairs = m & ((m << 1) | (prev ? 1ull : 0ull));
+        if (pairs) {
+            atomicOr(&status->nonquiet, 1u);
+            atomicMin(&status->first_nonquiet_block, (unsigned long long)tile * 64 + (__ffsll((long long)pairs) - 1));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exclusive scan of tile_bytes: groups of SCAN_G tiles
+// ------------------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 1024;
+constexpr int SCAN_PER = 4;
+constexpr int SCAN_G = SCAN_T * SCAN_PER;  // tiles per group
+
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* s_warp, uint64_t* total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint64_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += u; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = (lane < (blockDim.x >> 5)) ? s_warp[lane] : 0;
+        uint64_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint64_t u = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= (uint32_t)d) wi += u; }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    if (total) *total = s_warp[32];
+    return incl - v + s_warp[warp];
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_groups_local(const uint32_t* __restrict__ tile_bytes, uint32_t ntiles,
+                                                           uint32_t* __restrict__ tile_local, uint64_t* __restrict__ group_total) {
+    __shared__ uint64_t s_warp[33];
+    const uint32_t base = blockIdx.x * SCAN_G + threadIdx.x * SCAN_PER;
+    uint32_t v[SCAN_PER]; uint64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) { v[k] = (base + k < ntiles) ? tile_bytes[base + k] : 0u; sum += v[k]; }
+    uint64_t tot;
+    uint64_t ex = block_exclusive_scan_u64(sum, s_warp, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) { if (base + k < ntiles) tile_local[base + k] = (uint32_t)ex; ex += v[k]; }
+    if (threadIdx.x == 0) group_total[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_group_totals(const uint64_t* __restrict__ group_total, uint32_t ngroups,
+                                                           uint64_t* __restrict__ group_off, Status* __restrict__ status,
+                                                           uint64_t cap, uint64_t* __restrict__ d_out_size) {
+    __shared__ uint64_t s_warp[33];
+    __shared__ uint64_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ngroups; base += SCAN_T) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = (i < ngroups) ? group_total[i] : 0;
+        uint64_t tot;
+        uint64_t ex = block_exclusive_scan_u64(v, s_warp, &tot);
+        if (i < ngroups) group_off[i] = s_carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint64_t total = s_carry;
+        if (total > cap) { status->error = 2; total = 0; }  // DENSITY_B200_ECAPACITY
+        status->out_bytes = total;
+        if (d_out_size) *d_out_size = total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Pass 2: emit. One CTA (256 threads) per tile of 64 blocks; warp w handles block pairs w, w+8, ...
+// ------------------------------------------------------------------------------------------------------
+constexpr int EM_THREADS = 256;
+
+__global__ void __launch_bounds__(EM_THREADS)
+cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, const uint32_t* __restrict__ sigw_g,
+          const uint8_t* __restrict__ copymap, int use_copymap_if_nonquiet, const Status* __restrict__ status,
+          const uint32_t* __restrict__ tile_local, const uint64_t* __restrict__ group_off, uint8_t* __restrict__ out) {
+    if (status->error) return;
+    __shared__ uint32_t s_off[65];
+    __shared__ uint32_t s_sig[128];
+    __shared__ uint8_t s_copied[64];
+    __shared__ uint32_t s_wsum[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const bool use_cm = copymap && (!use_copymap_if_nonquiet || status->nonquiet);
+    const uint64_t tile_off = group_off[tile / SCAN_G] + tile_local[tile];
+    const uint64_t nquads = nbytes / 4;
+
+    if (tid < 64) {
+        const uint64_t b = (uint64_t)tile * 64 + tid;
+        uint32_t sz = 0, lo = 0, hi = 0; bool copied = false;
+        if (b < nblocks) {
+            copied = use_cm && copymap[b];
+            lo = sigw_g[2 * b]; hi = sigw_g[2 * b + 1];
+            sz = block_out_bytes(b, nbytes, __popc(lo) + __popc(hi), copied);
+        }
+        s_sig[2 * tid] = lo; s_sig[2 * tid + 1] = hi; s_copied[tid] = copied;
+        uint32_t incl = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += u; }
+        if (lane == 31) s_wsum[warp] = incl;
+        s_off[tid + 1] = incl;  // provisional (warp-local)
+    }
+    __syncthreads();
+    if (tid >= 32 && tid < 64) s_off[tid + 1] += s_wsum[0];
+    if (tid == 0) s_off[0] = 0;
+    __syncthreads();
+
+    const uint8_t* in_b = reinterpret_cast<const uint8_t*>(in);
+    for (uint32_t bp = warp; bp < 32; bp += EM_THREADS / 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t bl = bp * 2 + (j >> 1);                   // block within tile
+            const uint64_t b = (uint64_t)tile * 64 + bl;
+            if (b >= nblocks) continue;                               // warp-uniform
+            const uint32_t k = (j & 1) * 32 + lane;                   // quad index within block
+            const uint64_t gq = b * 64 + k;
+            uint8_t* const bout = out + tile_off + s_off[bl];
+            if (s_copied[bl]) {
+                // copy-mode block: raw bytes (codec.rs:36)
+                const uint64_t boff = b * 256;
+                const uint32_t blen = (uint32_t)((nbytes - boff < 256) ? (nbytes - boff) : 256);
+                if (gq < nquads && k * 4 + 4 <= blen) {
+                    uint32_t q = in[gq];
+                    st_u16(bout + 4 * k, q & 0xFFFFu); st_u16(bout + 4 * k + 2, q >> 16);
+                }
+                if ((j & 1) == 1 && lane < (blen & 3u)) bout[(blen & ~3u) + lane] = in_b[boff + (blen & ~3u) + lane];
+                continue;
+            }
+            const uint32_t lo = s_sig[2 * bl], hi = s_sig[2 * bl + 1];
+            if ((j & 1) == 0 && lane < 4) {
+                // signature, 8 bytes LE at the block start (codec.rs:24-26,40-41,67)
+                st_u16(bout + 2 * lane, ((lane < 2 ? lo : hi) >> (16 * (lane & 1))) & 0xFFFFu);
+            }
+            if (gq < nquads) {
+                const uint32_t q = in[gq];
+                const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
+                const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
+                uint8_t* p = bout + 8 + 4 * k - 2 * before;
+                if (flag) {
+                    st_u16(p, prod_hash(hash_prod(q)));               // chameleon.rs:97-98
+                } else {
+                    st_u16(p, q & 0xFFFFu); st_u16(p + 2, q >> 16);  // chameleon.rs:92-93
+                }
+            }
+            // 1..3 raw tail bytes after the last quad of the final block (codec.rs:58-61)
+            if ((j & 1) == 1 && b == nblocks - 1 && lane < (uint32_t)(nbytes & 3)) {
+                const uint64_t boff = b * 256;
+                const uint32_t blen = (uint32_t)(nbytes - boff);
+                const uint32_t nq = blen >> 2;
+                uint8_t* p = bout + 8 + 4 * nq - 2 * (__popc(lo) + __popc(hi));
+                p[lane] = in_b[boff + (blen & ~3u) + lane];
+            }
+        }
+    }
+}
+
+__global__ void cham_table_init_k(uint32_t* __restrict__ t) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536) t[i] = (i == 0) ? 0x10000u : 0u;  // stream start: bucket 0 "holds quad 0" (chameleon.rs:41,89-91)
+}
+__global__ void cham_table_fold_k(uint32_t* __restrict__ acc, const uint32_t* __restrict__ next) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536) { uint32_t v = next[i]; if (v & 0x10000u) acc[i] = v; }
+}
+
+}  // namespace cham
+
+// ------------------------------------------------------------------------------------------------------
+// host-side launch sequence
+// ------------------------------------------------------------------------------------------------------
+using namespace cham;
+
+size_t cham_workspace_bytes(size_t nbytes, int nruns_max, ChamLayout* L) {
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    const uint64_t ntiles = (nblocks + 63) / 64;
+    const uint64_t ngroups = (ntiles + SCAN_G - 1) / SCAN_G;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    L->status = take(sizeof(Status));
+    L->sigw = take((ntiles * 64 * 2 + 64) * sizeof(uint32_t));
+    L->copymap = take(ntiles * 64 + 64);
+    L->tile_bytes = take((ntiles + 1) * sizeof(uint32_t));
+    L->tile_local = take((ntiles + 1) * sizeof(uint32_t));
+    L->group_total = take((ngroups + 1) * sizeof(uint64_t));
+    L->group_off = take((ngroups + 1) * sizeof(uint64_t));
+    L->unres = take((size_t)nruns_max * 65536 * sizeof(uint2));
+    L->unres_count = take((size_t)nruns_max * sizeof(uint32_t));
+    L->final_tab = take((size_t)nruns_max * 65536 * sizeof(uint32_t));
+    L->carry = take((size_t)nruns_max * 65536 * sizeof(uint32_t));
+    L->total = off;
+    return off;
+}
+
+static cudaError_t set_smem_attrs_once() {
+    static bool done = false;
+    static cudaError_t err = cudaSuccess;
+    if (!done) {
+        err = cudaFuncSetAttribute(cham_flag_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlagSmem));
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(cham_protected_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProtSmem));
+        done = true;
+    }
+    return err;
+}
+
+uint32_t cham_pick_runs(size_t nbytes, int num_sms) {
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    const uint64_t ntiles = (nblocks + 63) / 64;
+    // at least 16 tiles (256 KiB) per run so that first-touch traffic stays small
+    uint64_t r = ntiles / 16;
+    if (r < 1) r = 1;
+    if (r > (uint64_t)num_sms) r = num_sms;
+    return (uint32_t)r;
+}
+
+// Phase 1 of the encode: flag pass over all runs + fold of the last-writer tables.
+cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
+                               uint32_t* d_table_out, cudaStream_t stream, uint64_t* launches) {
+    cudaError_t e = set_smem_attrs_once();
+    if (e != cudaSuccess) return e;
+    const uint64_t nquads = nbytes / 4;
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
+    Status* st = reinterpret_cast<Status*>(ws + L.status);
+    e = cudaMemsetAsync(st, 0, sizeof(Status), stream);
+    if (e != cudaSuccess) return e;
+    {
+        // first_nonquiet_block starts at ~0
+        e = cudaMemsetAsync(&st->first_nonquiet_block, 0xFF, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+    }
+    if (nblocks == 0) return cudaSuccess;
+    cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(
+        reinterpret_cast<const uint32_t*>(d_in), nquads, ntiles, nruns, reinterpret_cast<uint32_t*>(ws + L.sigw),
+        reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+        reinterpret_cast<uint32_t*>(ws + L.final_tab));
+    ++*launches;
+    if (d_table_out) {
+        // shard export: fold of this shard's runs with "nothing touched" as the initial state
+        cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), nullptr, 1, nruns,
+                                                        nullptr, d_table_out);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+// Phase 2: carry-in tables, resolve, sizes, scan, (protected fallback), emit.
+cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
+                               const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches) {
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
+    const uint32_t ngroups = (ntiles + SCAN_G - 1) / SCAN_G;
+    Status* st = reinterpret_cast<Status*>(ws + L.status);
+    uint32_t* sigw = reinterpret_cast<uint32_t*>(ws + L.sigw);
+    uint8_t* copymap = ws + L.copymap;
+    if (nblocks == 0) {
+        return cudaMemsetAsync(d_out_size, 0, sizeof(uint64_t), stream);
+    }
+    cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
+                                                    reinterpret_cast<uint32_t*>(ws + L.carry), nullptr);
+    ++*launches;
+    cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+                                                     reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw);
+    ++*launches;
+    const uint32_t ts_blocks = (ntiles + 7) / 8;
+    cham_tile_sizes<<<ts_blocks, 256, 0, stream>>>(sigw, nullptr, nbytes, nblocks, ntiles, 0, 1, assume_prev_inc ? 1 : 0, st,
+                                                   reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
+    ++*launches;
+    if (allow_protected_fallback) {
+        // Runs only when the quiet check failed: recompute signatures + copy map exactly, then the sizes again.
+        cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, st, 1, sigw, copymap);
+        ++*launches;
+        cham_tile_sizes<<<ts_blocks, 256, 0, stream>>>(sigw, copymap, nbytes, nblocks, ntiles, 1, 0, 0, st,
+                                                       reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
+        ++*launches;
+    }
+    scan_groups_local<<<ngroups, SCAN_T, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.tile_bytes), ntiles,
+                                                      reinterpret_cast<uint32_t*>(ws + L.tile_local),
+                                                      reinterpret_cast<uint64_t*>(ws + L.group_total));
+    ++*launches;
+    scan_group_totals<<<1, SCAN_T, 0, stream>>>(reinterpret_cast<uint64_t*>(ws + L.group_total), ngroups,
+                                                reinterpret_cast<uint64_t*>(ws + L.group_off), st, (uint64_t)cap, d_out_size);
+    ++*launches;
+    cham_emit<<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw,
+                                                 allow_protected_fallback ? copymap : nullptr, 1, st,
+                                                 reinterpret_cast<uint32_t*>(ws + L.tile_local),
+                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t cham_table_init(uint32_t* d_table, cudaStream_t stream, uint64_t* launches) {
+    cham_table_init_k<<<65536 / 256, 256, 0, stream>>>(d_table);
+    ++*launches;
+    return cudaGetLastError();
+}
+cudaError_t cham_table_fold(uint32_t* d_acc, const uint32_t* d_next, cudaStream_t stream, uint64_t* launches) {
+    cham_table_fold_k<<<65536 / 256, 256, 0, stream>>>(d_acc, d_next);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+// Exact sequential encode only (checker / forced fallback).
+cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out,
+                                       size_t cap, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches) {
+    cudaError_t e = set_smem_attrs_once();
+    if (e != cudaSuccess) return e;
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
+    const uint32_t ngroups = (ntiles + SCAN_G - 1) / SCAN_G;
+    Status* st = reinterpret_cast<Status*>(ws + L.status);
+    uint32_t* sigw = reinterpret_cast<uint32_t*>(ws + L.sigw);
+    uint8_t* copymap = ws + L.copymap;
+    e = cudaMemsetAsync(st, 0, sizeof(Status), stream);
+    if (e != cudaSuccess) return e;
+    if (nblocks == 0) return cudaMemsetAsync(d_out_size, 0, sizeof(uint64_t), stream);
+    cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, st, 0, sigw, copymap);
+    ++*launches;
+    cham_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(sigw, copymap, nbytes, nblocks, ntiles, 0, 0, 0, st,
+                                                          reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
+    ++*launches;
+    scan_groups_local<<<ngroups, SCAN_T, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.tile_bytes), ntiles,
+                                                      reinterpret_cast<uint32_t*>(ws + L.tile_local),
+                                                      reinterpret_cast<uint64_t*>(ws + L.group_total));
+    ++*launches;
+    scan_group_totals<<<1, SCAN_T, 0, stream>>>(reinterpret_cast<uint64_t*>(ws + L.group_total), ngroups,
+                                                reinterpret_cast<uint64_t*>(ws + L.group_off), st, (uint64_t)cap, d_out_size);
+    ++*launches;
+    cham_emit<<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw, copymap, 0, st,
+                                                 reinterpret_cast<uint32_t*>(ws + L.tile_local),
+                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace dns

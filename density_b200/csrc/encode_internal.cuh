@@ -1,0 +1,40 @@
+// encode_internal.cuh — host-side interfaces between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace dns {
+
+// byte offsets of the Chameleon encode scratch arrays inside one workspace allocation
+struct ChamLayout {
+    size_t status, sigw, copymap, tile_bytes, tile_local, group_total, group_off, unres, unres_count, final_tab, carry, total;
+};
+
+size_t cham_workspace_bytes(size_t nbytes, int nruns_max, ChamLayout* L);
+uint32_t cham_pick_runs(size_t nbytes, int num_sms);
+cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
+                               uint32_t* d_table_out, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
+                               const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out,
+                                       size_t cap, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
+
+// chameleon_decode.cu
+size_t cham_decode_workspace_bytes();
+cudaError_t cham_decode(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, uint64_t* d_out_size,
+                        cudaStream_t stream, uint64_t* launches);
+
+// scalar_codec.cu (Cheetah / Lion, in-order)
+size_t scalar_workspace_bytes(int alg);
+cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
+cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
+
+// table helpers (sharded API)
+cudaError_t cham_table_init(uint32_t* d_table, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_table_fold(uint32_t* d_acc, const uint32_t* d_next, cudaStream_t stream, uint64_t* launches);
+
+}  // namespace dns

@@ -1,0 +1,130 @@
+/*
+ * density_b200.h — C ABI of the B200-native (sm_100a) implementation of density's
+ * Chameleon / Cheetah / Lion encode/decode hot path.
+ *
+ * Drop-in boundary. The first nine symbols have exactly the names, signatures and
+ * semantics of the reference's own `extern "C"` exports, so a binary (or a Rust
+ * `extern "C"` block) that links against density-rs can link
+ * against libdensity_b200.so instead:
+ *
+ *   chameleon_encode / chameleon_decode / chameleon_safe_encode_buffer_size
+ *       replace /root/reference/src/algorithms/chameleon/chameleon.rs:70-83
+ *   cheetah_encode / cheetah_decode / cheetah_safe_encode_buffer_size
+ *       replace /root/reference/src/algorithms/cheetah/cheetah.rs:105-118
+ *   lion_encode / lion_decode / lion_safe_encode_buffer_size
+ *       replace /root/reference/src/algorithms/lion/lion.rs:193-206
+ *
+ * They take plain pointers and sizes. The pointers may be HOST pointers (pageable or
+ * pinned; the library stages through device memory) or DEVICE pointers (detected with
+ * cudaPointerGetAttributes; no staging). The call is synchronous and returns the number
+ * of bytes written, or 0 on any error (the reference maps Err -> 0 the same way,
+ * chameleon.rs:72 `unwrap_or(0)`; where the reference would panic on an undersized
+ * buffer — io/write_buffer.rs:19 — this library returns 0 and never writes out of bounds).
+ * Output is bit-identical to the reference's Codec::encode / Codec::decode
+ * (codec/codec.rs:72-126) on the same input.
+ *
+ * There is no CPU fallback: every entry point fails (returns 0 / an error code) when no
+ * CUDA device is usable.
+ */
+#ifndef DENSITY_B200_H
+#define DENSITY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DENSITY_B200_API __attribute__((visibility("default")))
+#else
+#define DENSITY_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- the reference's FFI surface (host or device pointers, synchronous) ---------------- */
+DENSITY_B200_API size_t chameleon_encode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+DENSITY_B200_API size_t chameleon_decode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+DENSITY_B200_API size_t chameleon_safe_encode_buffer_size(size_t size); /* codec/codec.rs:18-21 */
+
+DENSITY_B200_API size_t cheetah_encode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+DENSITY_B200_API size_t cheetah_decode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+DENSITY_B200_API size_t cheetah_safe_encode_buffer_size(size_t size);
+
+DENSITY_B200_API size_t lion_encode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+DENSITY_B200_API size_t lion_decode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+DENSITY_B200_API size_t lion_safe_encode_buffer_size(size_t size);
+
+/* ---- device-resident, stream-ordered variants (what bench.py times) --------------------- */
+#define DENSITY_B200_CHAMELEON 0
+#define DENSITY_B200_CHEETAH 1
+#define DENSITY_B200_LION 2
+
+#define DENSITY_B200_OK 0
+#define DENSITY_B200_ECUDA 1      /* a CUDA runtime call failed (see density_b200_last_error) */
+#define DENSITY_B200_ECAPACITY 2  /* output buffer too small */
+#define DENSITY_B200_EMALFORMED 3 /* truncated / malformed stream on decode */
+#define DENSITY_B200_EARG 4       /* bad argument (alignment, algorithm id, null pointer) */
+
+/*
+ * Encode `n` bytes at device pointer d_in (4-byte aligned) into d_out (2-byte aligned,
+ * capacity `cap` >= *_safe_encode_buffer_size(n)). All work is enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream); nothing is synchronised.
+ * The encoded size is written to *d_out_size (device memory, 8 bytes) when the stream
+ * reaches that point; it is 0 if the device-side capacity check failed.
+ * Returns DENSITY_B200_OK or an error code for failures detectable at enqueue time.
+ */
+DENSITY_B200_API int density_b200_encode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                               uint64_t* d_out_size, void* stream);
+/* Test/diagnostic variant: choose the Chameleon encode path explicitly.
+   path 0 = auto (segment-parallel fast path, exact protection-aware fallback when needed),
+   1 = fast path only (no fallback; out size is only valid if the stream is "quiet"),
+   2 = exact in-order protection-aware walk only, 3 = scalar reference kernel. */
+DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                    uint64_t* d_out_size, void* stream, int path);
+/* Same contract for decode; `cap` must be >= the original length. */
+DENSITY_B200_API int density_b200_decode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                               uint64_t* d_out_size, void* stream);
+
+/*
+ * Sharded Chameleon encode (one bit-exact stream cut across several GPUs / calls).
+ * The stream is cut at multiples of 256 bytes. Every shard runs phase 1 independently, the
+ * 256 KiB last-writer tables are exchanged by the caller (torch.distributed all_gather in
+ * density_b200/sharded.py), and phase 2 finishes the shard given the dictionary carried in
+ * from all earlier shards. The concatenation of the shard outputs equals the output of one
+ * chameleon_encode call over the concatenated input, provided the protection automaton stays
+ * quiet (reported through *d_flags bit 0 otherwise; the caller then falls back to one device).
+ */
+typedef struct density_b200_shard density_b200_shard; /* opaque */
+DENSITY_B200_API density_b200_shard* density_b200_shard_create(void);
+DENSITY_B200_API void density_b200_shard_destroy(density_b200_shard*);
+/* phase 1: flags with unknown carry-in; exports this shard's last-writer table (65536 x u32:
+   bit 16 = bucket touched, low 16 bits = fingerprint) to d_table_out. */
+DENSITY_B200_API int density_b200_shard_phase1(density_b200_shard*, const uint8_t* d_in, size_t n, int is_last_shard,
+                              uint32_t* d_table_out, void* stream);
+/* phase 2: d_carry_in = table state before this shard (65536 x u32, same encoding; for the first
+   shard pass NULL). Writes the shard's piece of the stream to d_out and its size to *d_out_size. */
+DENSITY_B200_API int density_b200_shard_phase2(density_b200_shard*, const uint32_t* d_carry_in, uint8_t* d_out, size_t cap,
+                              uint64_t* d_out_size, uint32_t* d_flags, void* stream);
+/* Fold shard tables left to right: d_acc = (d_next touched) ? d_next : d_acc, elementwise, 65536 entries.
+   d_acc == NULL-initialised state is produced by density_b200_table_init. */
+DENSITY_B200_API int density_b200_table_init(uint32_t* d_table, void* stream);
+DENSITY_B200_API int density_b200_table_fold(uint32_t* d_acc, const uint32_t* d_next, void* stream);
+
+/* ---- housekeeping ---------------------------------------------------------------------- */
+/* Last error message of the calling thread's most recent failing call ("" if none). */
+DENSITY_B200_API const char* density_b200_last_error(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+DENSITY_B200_API uint64_t density_b200_kernel_launches(void);
+/* 1 if the last Chameleon encode on this device used the segment-parallel fast path end to end,
+   0 if it had to fall back to the sequential protection-aware path. */
+DENSITY_B200_API int density_b200_last_encode_was_fast(void);
+/* Free all cached device workspaces. */
+DENSITY_B200_API void density_b200_shutdown(void);
+/* Library version string. */
+DENSITY_B200_API const char* density_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENSITY_B200_H */

@@ -1,0 +1,197 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (needs a B200: pytest -m gpu).
+
+Bit-exact bar: every byte of every encoded stream equals the oracle's; every decode equals the original."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ALGS, payload, sha256, splitmix_bytes
+
+pytestmark = pytest.mark.gpu
+
+TEST_DATA = b"test" * 31 + b"t"
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def codecs(torch_cuda):
+    import density_b200
+    density_b200.load()  # raises if the CUDA extension is missing
+    return density_b200.CODECS
+
+
+def gpu_encode(C, data):
+    out = np.zeros(max(1, C.safe_encode_buffer_size(data.size)), dtype=np.uint8)
+    n = C.encode(data, out)
+    return out[:n]
+
+
+def gpu_decode(C, enc, n):
+    out = np.zeros(max(1, n), dtype=np.uint8)
+    m = C.decode(enc, out)
+    return out[:m]
+
+
+@pytest.mark.parametrize("alg", ALGS)
+def test_reference_kats_through_c_abi(codecs, alg, golden):
+    C = codecs[alg]
+    data = np.frombuffer(TEST_DATA, dtype=np.uint8)
+    out = np.zeros(len(TEST_DATA), dtype=np.uint8)  # same undersized-but-sufficient buffer as lib.rs:24
+    n = C.encode(data, out)
+    assert out[:n].tolist() == golden["kat"]["alg"][alg]["bytes"]
+    assert gpu_decode(C, out[:n], len(TEST_DATA)).tobytes() == TEST_DATA
+
+
+@pytest.mark.parametrize("alg", ALGS)
+def test_golden_fixtures_encode_decode(codecs, alg, golden, golden_inputs):
+    C = codecs[alg]
+    for name, data in golden_inputs.items():
+        if name == "dickens_full":
+            continue
+        enc = gpu_encode(C, data)
+        e = golden[name]["alg"][alg]
+        assert (enc.size, sha256(enc)) == (e["size"], e["sha256"]), (alg, name)
+        dec = gpu_decode(C, enc, data.size)
+        assert dec.size == data.size and (dec == data).all(), (alg, name)
+
+
+@pytest.mark.parametrize("alg", ALGS)
+@pytest.mark.parametrize("kind", ["text", "random", "zeros", "low", "mixed"])
+def test_tail_and_copy_mode_sweep_vs_oracle(codecs, alg, kind):
+    C = codecs[alg]
+    for n in [1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 63, 64, 65, 127, 128, 129, 255, 256, 257, 260, 511, 512, 513, 1000, 2999,
+              16383, 16384, 16385, 16387, 70001]:
+        data = payload(kind, n, seed=n)
+        want = oracle.encode(alg, data)
+        got = gpu_encode(C, data)
+        assert got.size == want.size and (got == want).all(), (alg, kind, n)
+        dec = gpu_decode(C, got, n)
+        assert dec.size == n and (dec == data).all(), (alg, kind, n)
+
+
+@pytest.mark.parametrize("alg", ALGS)
+def test_empty_input(codecs, alg):
+    C = codecs[alg]
+    assert C.encode(np.zeros(0, np.uint8), np.zeros(8, np.uint8)) == 0
+    assert C.decode(np.zeros(0, np.uint8), np.zeros(8, np.uint8)) == 0
+
+
+@pytest.mark.parametrize("path", [0, 1, 2, 3])
+@pytest.mark.parametrize("nbytes", [300, 16 * 1024, 16 * 1024 + 4, 1 << 20, (1 << 22) + 777, 9 * (1 << 20) + 2])
+def test_chameleon_every_device_path_on_text(torch_cuda, codecs, path, nbytes):
+    """path 0 auto, 1 parallel fast path only, 2 in-order protected walk, 3 scalar kernel: all bit-identical on quiet text."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    if path == 3 and nbytes > (1 << 22) + 777:
+        pytest.skip("scalar kernel is slow")
+    data = synth.synth_text(nbytes).numpy()
+    want = oracle.encode("chameleon", data)
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(nbytes) + 64, dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("chameleon", d_in, d_out, d_sz, path=path)
+    torch.cuda.synchronize()
+    n = int(d_sz.item())
+    got = d_out[:n].cpu().numpy()
+    assert n == want.size and (got == want).all()
+
+
+@pytest.mark.parametrize("kind", ["random", "mixed", "low", "zeros"])
+@pytest.mark.parametrize("nbytes", [70001, 1 << 20, 3 * (1 << 20) + 5])
+def test_chameleon_non_quiet_inputs_fall_back_exactly(codecs, kind, nbytes):
+    C = codecs["chameleon"]
+    data = payload(kind, nbytes, seed=3)
+    want = oracle.encode("chameleon", data)
+    got = gpu_encode(C, data)
+    assert got.size == want.size and (got == want).all()
+
+
+def test_chameleon_many_runs_64mib_text(torch_cuda, codecs):
+    """148 runs of >=16 tiles each: exercises the carry-in / unresolved machinery across every SM."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    n = 64 * (1 << 20) + 1234
+    d_in = synth.synth_text(n, device="cuda")
+    data = d_in.cpu().numpy()
+    want = oracle.encode("chameleon", data)
+    d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("chameleon", d_in, d_out, d_sz, path=1)
+    torch.cuda.synchronize()
+    got = d_out[:int(d_sz.item())].cpu().numpy()
+    assert got.size == want.size and (got == want).all()
+    assert density_b200.load().density_b200_last_encode_was_fast() == 1
+
+
+def test_chameleon_full_size_1gib_text_bit_exact(torch_cuda, codecs):
+    """BASELINE.json configs[1] at full size: bit-exact against the oracle, plus the size-independent checks
+    (round trip of a prefix through the decoder; determinism across two runs)."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    n = 1 << 30
+    d_in = synth.synth_text(n, device="cuda")
+    d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("chameleon", d_in, d_out, d_sz)
+    torch.cuda.synchronize()
+    m = int(d_sz.item())
+    assert density_b200.load().density_b200_last_encode_was_fast() == 1
+    got = d_out[:m].cpu().numpy()
+    want = oracle.encode("chameleon", d_in.cpu().numpy())
+    assert m == want.size
+    assert (got == want).all()
+    # determinism
+    d_out2 = torch.zeros_like(d_out)
+    density_b200.encode_device("chameleon", d_in, d_out2, d_sz)
+    torch.cuda.synchronize()
+    assert int(d_sz.item()) == m and torch.equal(d_out[:m], d_out2[:m])
+
+
+@pytest.mark.parametrize("alg", ALGS)
+def test_device_pointers_through_reference_symbols(torch_cuda, codecs, alg):
+    torch = torch_cuda
+    C = codecs[alg]
+    data = payload("text", 50000, 5)
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.zeros(C.safe_encode_buffer_size(data.size), dtype=torch.uint8, device="cuda")
+    n = C.encode(d_in, d_out)
+    want = oracle.encode(alg, data)
+    assert n == want.size and (d_out[:n].cpu().numpy() == want).all()
+    d_dec = torch.zeros(data.size, dtype=torch.uint8, device="cuda")
+    m = C.decode(d_out[:n].clone(), d_dec)
+    assert m == data.size and (d_dec.cpu().numpy() == data).all()
+
+
+@pytest.mark.parametrize("alg", ALGS)
+def test_error_behaviour_returns_zero_never_aborts(codecs, alg):
+    from density_b200 import DecodeError, EncodeError
+    C = codecs[alg]
+    data = splitmix_bytes(4096, 11)
+    with pytest.raises(EncodeError):   # output too small for incompressible data: reference would panic (write_buffer.rs:19)
+        C.encode(data, np.zeros(1000, dtype=np.uint8))
+    enc = gpu_encode(C, payload("text", 4096, 2))
+    with pytest.raises(DecodeError):   # output too small
+        C.decode(enc, np.zeros(100, dtype=np.uint8))
+    with pytest.raises(DecodeError):   # truncated inside a signature
+        C.decode(enc[:3], np.zeros(4096, dtype=np.uint8))
+
+
+def test_decode_oracle_streams_and_vice_versa(codecs):
+    """Streams are interchangeable with the reference's in both directions."""
+    for alg in ALGS:
+        C = codecs[alg]
+        data = payload("mixed", 200000, 9)
+        enc_cpu = oracle.encode(alg, data)
+        assert (gpu_decode(C, enc_cpu, data.size) == data).all()
+        enc_gpu = gpu_encode(C, data)
+        assert (oracle.decode(alg, enc_gpu, data.size) == data).all()

@@ -24,6 +24,8 @@ _SIGS = {
     "density_b200_shard_phase2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "density_b200_table_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "density_b200_table_fold": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "density_b200_profile_enable": (None, [ctypes.c_int]),
+    "density_b200_profile_get": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "density_b200_last_error": (ctypes.c_char_p, []),
     "density_b200_kernel_launches": (ctypes.c_uint64, []),
     "density_b200_last_encode_was_fast": (ctypes.c_int, []),

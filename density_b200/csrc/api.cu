@@ -53,6 +53,9 @@ struct DeviceCtx {
     uint64_t* h_size = nullptr;        // 8 B pinned
     ChamLayout layout{};
     int last_was_chameleon_fastpath_capable = 0;
+    bool profile = false;              // record per-stage events (density_b200_profile_*)
+    bool profile_valid = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::mutex mu;
 };
 
@@ -113,9 +116,15 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
             e = cham_encode_protected_only(d_in, n, c->ws.p, L, d_out, cap, d_out_size, stream, &launches);
         } else {
             const uint32_t nruns = cham_pick_runs(n, c->num_sms);
-            e = cham_encode_phase1(d_in, n, c->ws.p, L, nruns, nullptr, stream, &launches);
+            cudaEvent_t* ev = nullptr;
+            if (c->profile) {
+                for (int i = 0; i < 4; ++i) if (!c->ev[i]) cudaEventCreate(&c->ev[i]);
+                ev = c->ev;
+            }
+            e = cham_encode_phase1(d_in, n, c->ws.p, L, nruns, nullptr, stream, &launches, ev);
             if (e == cudaSuccess)
-                e = cham_encode_phase2(d_in, n, c->ws.p, L, nruns, nullptr, d_out, cap, d_out_size, path == 0, false, stream, &launches);
+                e = cham_encode_phase2(d_in, n, c->ws.p, L, nruns, nullptr, d_out, cap, d_out_size, path == 0, false, stream, &launches, ev);
+            c->profile_valid = (ev != nullptr && e == cudaSuccess);
         }
         c->last_was_chameleon_fastpath_capable = (path != 2);
     } else {
@@ -286,7 +295,7 @@ int density_b200_shard_phase2(density_b200_shard* s, const uint32_t* d_carry_in,
     uint64_t launches = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e = cham_encode_phase2(s->d_in, s->n, s->ws.p, s->L, s->nruns, d_carry_in, d_out, cap, d_out_size, false,
-                                       d_carry_in != nullptr, st, &launches);
+                                       d_carry_in != nullptr, st, &launches, nullptr);
     if (e == cudaSuccess && d_flags) {
         if (s->n) e = cudaMemcpyAsync(d_flags, s->ws.p + s->L.status + offsetof(Status, nonquiet), sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
         else e = cudaMemsetAsync(d_flags, 0, sizeof(uint32_t), st);
@@ -307,6 +316,28 @@ int density_b200_table_fold(uint32_t* d_acc, const uint32_t* d_next, void* strea
     cudaError_t e = cham_table_fold(d_acc, d_next, reinterpret_cast<cudaStream_t>(stream), &l);
     g_launches += l;
     if (e != cudaSuccess) { set_error("table_fold", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+
+// ---- per-stage device timing of the last Chameleon encode (bench.py's roofline) -----------------------------
+void density_b200_profile_enable(int enable) {
+    DeviceCtx* c = current_ctx();
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->profile = enable != 0;
+    c->profile_valid = false;
+}
+// out[0] = flag pass ms, out[1] = between (carry/resolve/sizes/scan) ms, out[2] = emit ms. Returns 0 on success.
+int density_b200_profile_get(float* out_ms) {
+    DeviceCtx* c = current_ctx();
+    if (!c || !out_ms) return DENSITY_B200_EARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->profile_valid) return DENSITY_B200_EARG;
+    cudaError_t e = cudaEventSynchronize(c->ev[3]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&out_ms[0], c->ev[0], c->ev[1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&out_ms[1], c->ev[1], c->ev[2]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&out_ms[2], c->ev[2], c->ev[3]);
+    if (e != cudaSuccess) { set_error("profile_get", e); return DENSITY_B200_ECUDA; }
     return DENSITY_B200_OK;
 }
 
@@ -336,6 +367,7 @@ void density_b200_shutdown(void) {
         if (c.d_size) cudaFree(c.d_size);
         if (c.h_size) cudaFreeHost(c.h_size);
         if (c.stream) cudaStreamDestroy(c.stream);
+        for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
         c.d_size = nullptr; c.h_size = nullptr; c.stream = nullptr; c.ready = false;
     }
     if (cur >= 0) cudaSetDevice(cur);

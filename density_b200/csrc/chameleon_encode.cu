@@ -655,7 +655,7 @@ uint32_t cham_pick_runs(size_t nbytes, int num_sms) {
 
 // Phase 1 of the encode: flag pass over all runs + fold of the last-writer tables.
 cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
-                               uint32_t* d_table_out, cudaStream_t stream, uint64_t* launches) {
+                               uint32_t* d_table_out, cudaStream_t stream, uint64_t* launches, cudaEvent_t* ev) {
     cudaError_t e = set_smem_attrs_once();
     if (e != cudaSuccess) return e;
     const uint64_t nquads = nbytes / 4;
@@ -670,11 +670,13 @@ cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
         if (e != cudaSuccess) return e;
     }
     if (nblocks == 0) return cudaSuccess;
+    if (ev) cudaEventRecord(ev[0], stream);
     cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(
         reinterpret_cast<const uint32_t*>(d_in), nquads, ntiles, nruns, reinterpret_cast<uint32_t*>(ws + L.sigw),
         reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
         reinterpret_cast<uint32_t*>(ws + L.final_tab));
     ++*launches;
+    if (ev) cudaEventRecord(ev[1], stream);
     if (d_table_out) {
         // shard export: fold of this shard's runs with "nothing touched" as the initial state
         cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), nullptr, 1, nruns,
@@ -687,7 +689,8 @@ cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
 // Phase 2: carry-in tables, resolve, sizes, scan, (protected fallback), emit.
 cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
                                const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
-                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches) {
+                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches,
+                               cudaEvent_t* ev) {
     const uint64_t nblocks = (nbytes + 255) / 256;
     const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
     const uint32_t ngroups = (ntiles + SCAN_G - 1) / SCAN_G;
@@ -722,11 +725,13 @@ cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
     scan_group_totals<<<1, SCAN_T, 0, stream>>>(reinterpret_cast<uint64_t*>(ws + L.group_total), ngroups,
                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), st, (uint64_t)cap, d_out_size);
     ++*launches;
+    if (ev) cudaEventRecord(ev[2], stream);
     cham_emit<<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw,
                                                  allow_protected_fallback ? copymap : nullptr, 1, st,
                                                  reinterpret_cast<uint32_t*>(ws + L.tile_local),
                                                  reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
     ++*launches;
+    if (ev) cudaEventRecord(ev[3], stream);
     return cudaGetLastError();
 }
 

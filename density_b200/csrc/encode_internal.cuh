@@ -14,10 +14,11 @@ struct ChamLayout {
 size_t cham_workspace_bytes(size_t nbytes, int nruns_max, ChamLayout* L);
 uint32_t cham_pick_runs(size_t nbytes, int num_sms);
 cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
-                               uint32_t* d_table_out, cudaStream_t stream, uint64_t* launches);
+                               uint32_t* d_table_out, cudaStream_t stream, uint64_t* launches, cudaEvent_t* ev = nullptr);
 cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
                                const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
-                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches);
+                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches,
+                               cudaEvent_t* ev = nullptr);
 cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out,
                                        size_t cap, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
 

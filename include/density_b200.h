@@ -111,6 +111,13 @@ DENSITY_B200_API int density_b200_shard_phase2(density_b200_shard*, const uint32
 DENSITY_B200_API int density_b200_table_init(uint32_t* d_table, void* stream);
 DENSITY_B200_API int density_b200_table_fold(uint32_t* d_acc, const uint32_t* d_next, void* stream);
 
+/* ---- per-stage device timing of the last Chameleon encode on the current device ------- */
+/* When enabled, density_b200_encode_device records CUDA events on the caller's stream around the flag pass
+   and the emit pass. density_b200_profile_get waits for them and returns
+   out_ms[0] = flag pass, out_ms[1] = carry/resolve/sizes/scan, out_ms[2] = emit (milliseconds). */
+DENSITY_B200_API void density_b200_profile_enable(int enable);
+DENSITY_B200_API int density_b200_profile_get(float* out_ms);
+
 /* ---- housekeeping ---------------------------------------------------------------------- */
 /* Last error message of the calling thread's most recent failing call ("" if none). */
 DENSITY_B200_API const char* density_b200_last_error(void);

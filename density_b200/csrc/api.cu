@@ -54,8 +54,9 @@ struct DeviceCtx {
     ChamLayout layout{};
     int last_was_chameleon_fastpath_capable = 0;
     bool profile = false;              // record per-stage events (density_b200_profile_*)
-    bool profile_valid = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int PROF_RING = 64;
+    cudaEvent_t ev[PROF_RING][4] = {};
+    uint64_t prof_count = 0;           // encodes recorded since profile_enable(1)
     std::mutex mu;
 };
 
@@ -118,13 +119,13 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
             const uint32_t nruns = cham_pick_runs(n, c->num_sms);
             cudaEvent_t* ev = nullptr;
             if (c->profile) {
-                for (int i = 0; i < 4; ++i) if (!c->ev[i]) cudaEventCreate(&c->ev[i]);
-                ev = c->ev;
+                ev = c->ev[c->prof_count % DeviceCtx::PROF_RING];
+                for (int i = 0; i < 4; ++i) if (!ev[i]) cudaEventCreate(&ev[i]);
             }
             e = cham_encode_phase1(d_in, n, c->ws.p, L, nruns, nullptr, stream, &launches, ev);
             if (e == cudaSuccess)
                 e = cham_encode_phase2(d_in, n, c->ws.p, L, nruns, nullptr, d_out, cap, d_out_size, path == 0, false, stream, &launches, ev);
-            c->profile_valid = (ev != nullptr && e == cudaSuccess);
+            if (ev != nullptr && e == cudaSuccess) c->prof_count++;
         }
         c->last_was_chameleon_fastpath_capable = (path != 2);
     } else {
@@ -325,19 +326,28 @@ void density_b200_profile_enable(int enable) {
     if (!c) return;
     std::lock_guard<std::mutex> lk(c->mu);
     c->profile = enable != 0;
-    c->profile_valid = false;
+    c->prof_count = 0;
 }
 // out[0] = flag pass ms, out[1] = between (carry/resolve/sizes/scan) ms, out[2] = emit ms. Returns 0 on success.
 int density_b200_profile_get(float* out_ms) {
     DeviceCtx* c = current_ctx();
     if (!c || !out_ms) return DENSITY_B200_EARG;
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->profile_valid) return DENSITY_B200_EARG;
-    cudaError_t e = cudaEventSynchronize(c->ev[3]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&out_ms[0], c->ev[0], c->ev[1]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&out_ms[1], c->ev[1], c->ev[2]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&out_ms[2], c->ev[2], c->ev[3]);
+    if (c->prof_count == 0) return DENSITY_B200_EARG;
+    const int nset = (int)(c->prof_count < (uint64_t)DeviceCtx::PROF_RING ? c->prof_count : DeviceCtx::PROF_RING);
+    double acc[3] = {0, 0, 0};
+    cudaError_t e = cudaSuccess;
+    for (int s = 0; s < nset && e == cudaSuccess; ++s) {
+        cudaEvent_t* ev = c->ev[s];
+        float ms[3];
+        e = cudaEventSynchronize(ev[3]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[2], ev[2], ev[3]);
+        for (int k = 0; k < 3; ++k) acc[k] += ms[k];
+    }
     if (e != cudaSuccess) { set_error("profile_get", e); return DENSITY_B200_ECUDA; }
+    for (int k = 0; k < 3; ++k) out_ms[k] = (float)(acc[k] / nset);
     return DENSITY_B200_OK;
 }
 
@@ -367,7 +377,7 @@ void density_b200_shutdown(void) {
         if (c.d_size) cudaFree(c.d_size);
         if (c.h_size) cudaFreeHost(c.h_size);
         if (c.stream) cudaStreamDestroy(c.stream);
-        for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
+        for (auto& set : c.ev) for (auto& e : set) if (e) { cudaEventDestroy(e); e = nullptr; }
         c.d_size = nullptr; c.h_size = nullptr; c.stream = nullptr; c.ready = false;
     }
     if (cur >= 0) cudaSetDevice(cur);

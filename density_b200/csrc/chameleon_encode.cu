@@ -44,16 +44,21 @@ constexpr int TILE_Q = FP_THREADS * FP_QPT;        // 4096 quads = 16 KiB = 64 b
 constexpr int SIDE_N = 8192;                       // first-misser table (u32), indexed by hash & (SIDE_N-1)
 constexpr uint32_t SIDE_EMPTY = 0xFFFFFFFFu;
 
+constexpr int CLS_N = 32;                          // slow-path classes: class = hash >> 11, one warp each
+constexpr int CLS_CAP = 128;                       // entries per class list; overflow -> sequential fallback
+
 struct FlagSmem {
     uint16_t tab[65536];          // fingerprint of the last quad seen in each bucket
     uint32_t vbit[2048];          // "bucket touched" for the one case tab cannot express (fingerprint 0)
     uint32_t conf[2048];          // per-tile conflict bits (bucket interleaves different values)
     uint32_t side[SIDE_N];        // per-tile min over missers of (pos << 16 | hash)
     uint2 slowdata[TILE_Q];       // published by slow members: {hash | fp << 16, old | touched << 16}
-    uint16_t slowlist[TILE_Q];    // positions of slow members, ascending
+    uint16_t cls_list[CLS_N][CLS_CAP];  // positions of the slow members of each class (unordered)
+    uint32_t cls_count[CLS_N];
     uint32_t slowmap[TILE_Q / 32];
     uint32_t sigw[TILE_Q / 32];   // flag bits of the tile: word (w*4+j) = ballot of warp w, sub-row j
     uint32_t unres_count;
+    uint32_t cls_overflow;
 };
 static_assert(sizeof(FlagSmem) <= 227 * 1024, "flag pass shared memory");
 
@@ -62,7 +67,7 @@ enum : uint32_t { ST_ACTIVE = 1, ST_TOUCHED = 2, ST_MISS = 4, ST_SLOW = 8, ST_FL
 
 __device__ __forceinline__ bool bit_test(const uint32_t* bm, uint32_t i) { return (bm[i >> 5] >> (i & 31)) & 1u; }
 
-// Append the lanes with `pred` set to the run's unresolved list (warp-aggregated).
+// Append the lanes with `pred` set to the run's unresolved list (warp-aggregated). Must be called by all 32 lanes.
 __device__ __forceinline__ void append_unres(bool pred, uint32_t qidx_in_run, uint32_t h, uint32_t f,
                                              uint32_t* s_count, uint2* __restrict__ unres_run) {
     uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
@@ -74,6 +79,54 @@ __device__ __forceinline__ void append_unres(bool pred, uint32_t qidx_in_run, ui
     if (pred) {
         uint32_t idx = base + __popc(m & lanemask_lt());
         if (idx < 65536u) unres_run[idx] = make_uint2(qidx_in_run, h | (f << 16));
+    }
+}
+
+// Sequential in-order resolution of ALL slow members of the tile by one warp (fallback when a class list
+// overflows: adversarial inputs that put hundreds of interleaving quads into a few buckets).
+__device__ __noinline__ void slow_path_sequential(FlagSmem& S, uint16_t* slowlist /* TILE_Q entries, aliases cls_list */,
+                                                  uint32_t run_q0, uint2* __restrict__ unres_run) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t ws[4] = {S.slowmap[lane * 4 + 0], S.slowmap[lane * 4 + 1], S.slowmap[lane * 4 + 2], S.slowmap[lane * 4 + 3]};
+    uint32_t cnt = __popc(ws[0]) + __popc(ws[1]) + __popc(ws[2]) + __popc(ws[3]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+    const uint32_t nslow = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t o = incl - cnt;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t m = ws[k];
+        while (m) { uint32_t b = __ffs(m) - 1; m &= m - 1; slowlist[o++] = (uint16_t)((lane * 4 + k) * 32 + b); }
+    }
+    __syncwarp();
+    // restore the pre-tile value of every slow bucket (all members of a bucket carry the same `old`)
+    for (uint32_t i = lane; i < nslow; i += 32) { uint2 d = S.slowdata[slowlist[i]]; S.tab[d.x & 0xFFFFu] = (uint16_t)(d.y & 0xFFFFu); }
+    __syncwarp();
+    for (uint32_t c = 0; c < nslow; c += 32) {
+        const uint32_t i = c + lane;
+        const bool valid = i < nslow;
+        uint32_t pos = 0, hh = 0x10000u + lane, ff = 0;
+        if (valid) { pos = slowlist[i]; uint2 d = S.slowdata[pos]; hh = d.x & 0xFFFFu; ff = d.x >> 16; }
+        uint32_t cur = 0; bool touched = false;
+        if (valid) { cur = S.tab[hh]; touched = cur != 0 || bit_test(S.vbit, hh); }
+        const uint32_t grp = __match_any_sync(0xFFFFFFFFu, hh);
+        const uint32_t lower = grp & lanemask_lt();
+        const int pl = lower ? 31 - __clz(lower) : 0;
+        const uint32_t fprev = __shfl_sync(0xFFFFFFFFu, ff, pl);
+        const bool hit = lower ? (fprev == ff) : (touched && cur == ff);
+        const bool is_last = (grp & lanemask_gt()) == 0;
+        const bool unres_here = valid && !lower && !touched;
+        if (valid) {
+            if (hit) atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));
+            if (is_last && (lower || !hit)) {
+                S.tab[hh] = (uint16_t)ff;
+                if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+            }
+        }
+        append_unres(unres_here, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
+        __syncwarp();
     }
 }
 
@@ -91,6 +144,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
     const uint64_t t_begin = (uint64_t)run * tiles_total / nruns;
     const uint64_t t_end = (uint64_t)(run + 1) * tiles_total / nruns;
     uint2* __restrict__ unres_run = unres + (size_t)run * 65536;
+    const uint32_t pos0 = warp * 128 + lane;  // position of my sub-row 0 quad inside a tile; sub-row j adds 32*j
 
     // ---- init shared state -------------------------------------------------------------------------
     {
@@ -99,33 +153,34 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         for (uint32_t i = tid; i < 65536 * 2 / 16; i += FP_THREADS) t4[i] = z;
         for (uint32_t i = tid; i < 2048; i += FP_THREADS) { S.vbit[i] = 0; S.conf[i] = 0; }
         for (uint32_t i = tid; i < SIDE_N; i += FP_THREADS) S.side[i] = SIDE_EMPTY;
-        if (tid == 0) S.unres_count = 0;
+        if (tid < CLS_N) S.cls_count[tid] = 0;
+        if (tid == 0) { S.unres_count = 0; S.cls_overflow = 0; }
     }
     __syncthreads();
 
     // ---- prefetch the first tile --------------------------------------------------------------------
     uint32_t nxt[FP_QPT];
+    {
+        const uint64_t q0 = t_begin * TILE_Q;
+        const uint32_t rem = (t_begin < t_end && q0 < nquads) ? (uint32_t)((nquads - q0 < TILE_Q) ? (nquads - q0) : TILE_Q) : 0u;
 #pragma unroll
-    for (int j = 0; j < FP_QPT; ++j) {
-        uint64_t gi = t_begin * TILE_Q + warp * 128 + j * 32 + lane;
-        nxt[j] = (t_begin < t_end && gi < nquads) ? ld_stream_u32(in + gi) : 0u;
+        for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < rem) ? ld_stream_u32(in + q0 + pos0 + 32 * j) : 0u;
     }
 
     for (uint64_t t = t_begin; t < t_end; ++t) {
         uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT], old[FP_QPT], st[FP_QPT];
         const uint64_t tile_q0 = t * TILE_Q;
+        const uint32_t rem = (tile_q0 < nquads) ? (uint32_t)((nquads - tile_q0 < TILE_Q) ? (nquads - tile_q0) : TILE_Q) : 0u;
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            q[j] = nxt[j];
-            uint64_t gi = tile_q0 + warp * 128 + j * 32 + lane;
-            st[j] = (gi < nquads) ? ST_ACTIVE : 0u;
-        }
-        // prefetch next tile (register double buffer; consumed one full tile later)
+        for (int j = 0; j < FP_QPT; ++j) { q[j] = nxt[j]; st[j] = (pos0 + 32 * j < rem) ? ST_ACTIVE : 0u; }
+        {   // prefetch next tile (register double buffer; consumed one full tile later)
+            const uint64_t q0 = tile_q0 + TILE_Q;
+            const uint32_t nrem = (t + 1 < t_end && q0 < nquads) ? (uint32_t)((nquads - q0 < TILE_Q) ? (nquads - q0) : TILE_Q) : 0u;
+            const uint32_t* __restrict__ np = in + q0 + pos0;
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            uint64_t gi = (t + 1) * TILE_Q + warp * 128 + j * 32 + lane;
-            nxt[j] = (t + 1 < t_end && gi < nquads) ? ld_stream_u32(in + gi) : 0u;
+            for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nrem) ? ld_stream_u32(np + 32 * j) : 0u;
         }
+        if (tid == 0) S.cls_overflow = 0;  // last read before the previous S5; next written in phase D
 
         // ---- phase A: read the pre-tile dictionary --------------------------------------------------
 #pragma unroll
@@ -150,8 +205,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         for (int j = 0; j < FP_QPT; ++j) {
             if (st[j] & ST_MISS) {
                 S.tab[h[j]] = (uint16_t)f[j];  // racy between different values on purpose
-                uint32_t pos = warp * 128 + j * 32 + lane;
-                atomicMin(&S.side[h[j] & (SIDE_N - 1)], (pos << 16) | h[j]);
+                atomicMin(&S.side[h[j] & (SIDE_N - 1)], ((pos0 + 32 * j) << 16) | h[j]);
             }
         }
         __syncthreads();  // S2
@@ -160,7 +214,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 #pragma unroll
         for (int j = 0; j < FP_QPT; ++j) {
             if (!(st[j] & ST_ACTIVE)) continue;
-            const uint32_t pos = warp * 128 + j * 32 + lane;
+            const uint32_t pos = pos0 + 32 * j;
             const uint32_t w = S.tab[h[j]];
             if (!(st[j] & ST_MISS)) {
                 // hit member: the bucket still holds my value unless some misser published (its value != mine)
@@ -183,10 +237,10 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         }
         __syncthreads();  // S3
 
-        // ---- phase D: classify, publish slow members, restore their buckets --------------------------
+        // ---- phase D: classify; slow members publish themselves into their class list ----------------
 #pragma unroll
         for (int j = 0; j < FP_QPT; ++j) {
-            const uint32_t pos = warp * 128 + j * 32 + lane;
+            const uint32_t pos = pos0 + 32 * j;
             if (st[j] & ST_TENT) {
                 if (bit_test(S.conf, h[j])) {
                     st[j] |= ST_SLOW;
@@ -201,7 +255,9 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             if (st[j] & ST_MISS) S.side[h[j] & (SIDE_N - 1)] = SIDE_EMPTY;
             if (st[j] & ST_SLOW) {
                 S.slowdata[pos] = make_uint2(h[j] | (f[j] << 16), old[j] | ((st[j] & ST_TOUCHED) ? 0x10000u : 0u));
-                S.tab[h[j]] = (uint16_t)old[j];  // every slow member of a bucket writes the same pre-tile value
+                const uint32_t c = h[j] >> 11;
+                const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
+                if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)pos; else S.cls_overflow = 1;
             }
             uint32_t sb = __ballot_sync(0xFFFFFFFFu, (st[j] & ST_SLOW) != 0);
             uint32_t fb = __ballot_sync(0xFFFFFFFFu, (st[j] & ST_FLAG) != 0);
@@ -209,55 +265,51 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         }
         __syncthreads();  // S4
 
-        // ---- phase F: unresolved appends, conflict-bit cleanup, slow path (warp 0) -------------------
+        // ---- phase F: unresolved appends, conflict-bit cleanup, slow members (warp w <- class w) -----
         const uint32_t run_q0 = (uint32_t)((t - t_begin) * TILE_Q);
+        if (__any_sync(0xFFFFFFFFu, ((st[0] | st[1] | st[2] | st[3]) & (ST_UNRES | ST_SETTER)) != 0)) {
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            append_unres((st[j] & ST_UNRES) != 0, run_q0 + warp * 128 + j * 32 + lane, h[j], f[j], &S.unres_count, unres_run);
-            if (st[j] & ST_SETTER) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
-        }
-        if (warp == 0) {
-            // position-sorted list of slow members from the bitmap
-            uint32_t w0 = S.slowmap[lane * 4 + 0], w1 = S.slowmap[lane * 4 + 1], w2 = S.slowmap[lane * 4 + 2], w3 = S.slowmap[lane * 4 + 3];
-            uint32_t cnt = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += v; }
-            const uint32_t nslow = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (nslow) {
-                uint32_t o = incl - cnt;
-                uint32_t ws[4] = {w0, w1, w2, w3};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t m = ws[k];
-                    while (m) { uint32_t b = __ffs(m) - 1; m &= m - 1; S.slowlist[o++] = (uint16_t)((lane * 4 + k) * 32 + b); }
-                }
-                __syncwarp();
-                for (uint32_t c = 0; c < nslow; c += 32) {
-                    const uint32_t i = c + lane;
-                    const bool valid = i < nslow;
-                    uint32_t pos = 0, hh = 0x10000u + lane, ff = 0;
-                    if (valid) { pos = S.slowlist[i]; uint2 d = S.slowdata[pos]; hh = d.x & 0xFFFFu; ff = d.x >> 16; }
-                    uint32_t cur = 0; bool touched = false;
-                    if (valid) { cur = S.tab[hh]; touched = cur != 0 || bit_test(S.vbit, hh); }
-                    const uint32_t grp = __match_any_sync(0xFFFFFFFFu, hh);
-                    const uint32_t lower = grp & lanemask_lt();
-                    const int pl = lower ? 31 - __clz(lower) : 0;
-                    const uint32_t fprev = __shfl_sync(0xFFFFFFFFu, ff, pl);
-                    const bool hit = lower ? (fprev == ff) : (touched && cur == ff);
-                    const bool is_last = (grp & lanemask_gt()) == 0;
-                    const bool unres_here = valid && !lower && !touched;
-                    if (valid) {
-                        if (hit) atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));
-                        if (is_last && (lower || !hit)) {
-                            S.tab[hh] = (uint16_t)ff;
-                            if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-                        }
-                    }
-                    append_unres(unres_here, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
-                    __syncwarp();
-                }
+            for (int j = 0; j < FP_QPT; ++j) {
+                append_unres((st[j] & ST_UNRES) != 0, run_q0 + pos0 + 32 * j, h[j], f[j], &S.unres_count, unres_run);
+                if (st[j] & ST_SETTER) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
             }
+        }
+        if (S.cls_overflow) {
+            if (warp == 0) slow_path_sequential(S, &S.cls_list[0][0], run_q0, unres_run);
+            if (warp == 1 && lane < CLS_N) S.cls_count[lane] = 0;
+        } else {
+            // In-order semantics per bucket: my predecessor is the member of my bucket with the largest smaller
+            // position; without one the pre-tile value `old` decides. The last member leaves its value behind.
+            const uint32_t n = S.cls_count[warp];
+            const uint16_t* __restrict__ lst = S.cls_list[warp];
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < n;
+                uint32_t pos = 0, hh = 0xFFFFFFFFu, ff = 0, oldv = 0; bool touched = false;
+                if (valid) {
+                    pos = lst[i];
+                    const uint2 d = S.slowdata[pos];
+                    hh = d.x & 0xFFFFu; ff = d.x >> 16; oldv = d.y & 0xFFFFu; touched = (d.y >> 16) & 1u;
+                }
+                int best = -1; uint32_t bestf = 0; bool later = false;
+                for (uint32_t k = 0; k < n; ++k) {
+                    const uint32_t pk = lst[k];          // broadcast reads
+                    const uint2 dk = S.slowdata[pk];
+                    if ((dk.x & 0xFFFFu) == hh) {
+                        if (pk < pos && (int)pk > best) { best = (int)pk; bestf = dk.x >> 16; }
+                        later |= pk > pos;
+                    }
+                }
+                const bool hit = valid && (best >= 0 ? (bestf == ff) : (touched && oldv == ff));
+                if (hit) atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));
+                if (valid && !later) {
+                    S.tab[hh] = (uint16_t)ff;
+                    if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                }
+                append_unres(valid && best < 0 && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
+            }
+            __syncwarp();
+            if (lane == 0) S.cls_count[warp] = 0;
         }
         __syncthreads();  // S5: dictionary final for this tile, sigw final
 

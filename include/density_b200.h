@@ -113,7 +113,8 @@ DENSITY_B200_API int density_b200_table_fold(uint32_t* d_acc, const uint32_t* d_
 
 /* ---- per-stage device timing of the last Chameleon encode on the current device ------- */
 /* When enabled, density_b200_encode_device records CUDA events on the caller's stream around the flag pass
-   and the emit pass. density_b200_profile_get waits for them and returns
+   and the emit pass of every call (ring of 64 calls; enable(1) resets it). density_b200_profile_get waits
+   for them and returns the per-call AVERAGE over the recorded calls:
    out_ms[0] = flag pass, out_ms[1] = carry/resolve/sizes/scan, out_ms[2] = emit (milliseconds). */
 DENSITY_B200_API void density_b200_profile_enable(int enable);
 DENSITY_B200_API int density_b200_profile_get(float* out_ms);

@@ -114,6 +114,40 @@ def test_chameleon_non_quiet_inputs_fall_back_exactly(codecs, kind, nbytes):
     assert got.size == want.size and (got == want).all()
 
 
+def _same_bucket_pair():
+    M = 0x9D6EF916
+    seen = {}
+    q = 0x12345678
+    while True:
+        q = (q * 1103515245 + 12345) & 0xFFFFFFFF
+        h = ((q * M) & 0xFFFFFFFF) >> 16
+        if h in seen and seen[h] != q:
+            return seen[h], q
+        seen[h] = q
+
+
+@pytest.mark.parametrize("path", [0, 1, 2])
+def test_chameleon_adversarial_same_bucket_alternation(torch_cuda, codecs, path):
+    """Thousands of interleaving quads in ONE hash bucket per tile (class-list overflow -> sequential in-tile fallback),
+    padded with zero runs so that every block stays compressible and the stream stays on the parallel path."""
+    torch = torch_cuda
+    import density_b200
+    q1, q2 = _same_bucket_pair()
+    block = np.array([q1, q2] * 20 + [0] * 24, dtype=np.uint32)
+    data = np.tile(block, 3000).view(np.uint8)[: 3000 * 256 - 3]
+    want, copied = oracle.encode("chameleon", data, return_copied=True)
+    assert copied == 0
+    d_in = torch.from_numpy(data.copy()).cuda()
+    d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(data.size) + 64, dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("chameleon", d_in, d_out, d_sz, path=path)
+    torch.cuda.synchronize()
+    n = int(d_sz.item())
+    assert n == want.size and (d_out[:n].cpu().numpy() == want).all()
+    if path == 1:
+        assert density_b200.load().density_b200_last_encode_was_fast() == 1
+
+
 def test_chameleon_many_runs_64mib_text(torch_cuda, codecs):
     """148 runs of >=16 tiles each: exercises the carry-in / unresolved machinery across every SM."""
     torch = torch_cuda

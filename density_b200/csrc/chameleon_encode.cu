@@ -45,25 +45,27 @@ constexpr int SIDE_N = 8192;                       // first-misser table (u32), 
 constexpr uint32_t SIDE_EMPTY = 0xFFFFFFFFu;
 
 constexpr int CLS_N = 32;                          // slow-path classes: class = hash >> 11, one warp each
-constexpr int CLS_CAP = 128;                       // entries per class list; overflow -> sequential fallback
+constexpr int CLS_CAP = 128;                       // entries per class list; overflow -> in-order tile fallback
+
+// Compacted per-tile record of a misser (or of a hit member that turned out to need the slow path):
+//   x = hash | fp << 16
+//   y = pos(12) | touched << 12 | slow << 13 | first << 14 | setter << 15 | old_fp << 16
+constexpr uint32_t R_TOUCHED = 1u << 12, R_SLOW = 1u << 13, R_FIRST = 1u << 14, R_SETTER = 1u << 15;
 
 struct FlagSmem {
     uint16_t tab[65536];          // fingerprint of the last quad seen in each bucket
     uint32_t vbit[2048];          // "bucket touched" for the one case tab cannot express (fingerprint 0)
     uint32_t conf[2048];          // per-tile conflict bits (bucket interleaves different values)
     uint32_t side[SIDE_N];        // per-tile min over missers of (pos << 16 | hash)
-    uint2 slowdata[TILE_Q];       // published by slow members: {hash | fp << 16, old | touched << 16}
-    uint16_t cls_list[CLS_N][CLS_CAP];  // positions of the slow members of each class (unordered)
+    uint2 rec[TILE_Q];            // records: missers (phase A) then slow hit members (phase C); quad staging in the fallback
+    uint16_t cls_list[CLS_N][CLS_CAP];  // record indices of the slow members of each class (unordered)
     uint32_t cls_count[CLS_N];
-    uint32_t slowmap[TILE_Q / 32];
-    uint32_t sigw[TILE_Q / 32];   // flag bits of the tile: word (w*4+j) = ballot of warp w, sub-row j
+    uint32_t sigw[TILE_Q / 32];   // flag bits of the tile: word (w*4+j) = sub-row j of warp w
+    uint32_t nrec;
     uint32_t unres_count;
     uint32_t cls_overflow;
 };
 static_assert(sizeof(FlagSmem) <= 227 * 1024, "flag pass shared memory");
-
-// status bits kept per quad in a register
-enum : uint32_t { ST_ACTIVE = 1, ST_TOUCHED = 2, ST_MISS = 4, ST_SLOW = 8, ST_FLAG = 16, ST_UNRES = 32, ST_SETTER = 64, ST_FIRST = 128, ST_TENT = 256 };
 
 __device__ __forceinline__ bool bit_test(const uint32_t* bm, uint32_t i) { return (bm[i >> 5] >> (i & 31)) & 1u; }
 
@@ -82,50 +84,33 @@ __device__ __forceinline__ void append_unres(bool pred, uint32_t qidx_in_run, ui
     }
 }
 
-// Sequential in-order resolution of ALL slow members of the tile by one warp (fallback when a class list
-// overflows: adversarial inputs that put hundreds of interleaving quads into a few buckets).
-__device__ __noinline__ void slow_path_sequential(FlagSmem& S, uint16_t* slowlist /* TILE_Q entries, aliases cls_list */,
-                                                  uint32_t run_q0, uint2* __restrict__ unres_run) {
+// In-order walk of one whole tile by one warp, from the (restored) pre-tile dictionary. Fallback for tiles whose
+// class lists overflow (adversarial inputs: hundreds of interleaving quads in a handful of buckets).
+__device__ __noinline__ void tile_in_order(FlagSmem& S, const uint32_t* qs, uint32_t rem, uint32_t run_q0,
+                                           uint2* __restrict__ unres_run) {
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t ws[4] = {S.slowmap[lane * 4 + 0], S.slowmap[lane * 4 + 1], S.slowmap[lane * 4 + 2], S.slowmap[lane * 4 + 3]};
-    uint32_t cnt = __popc(ws[0]) + __popc(ws[1]) + __popc(ws[2]) + __popc(ws[3]);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += v; }
-    const uint32_t nslow = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    uint32_t o = incl - cnt;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        uint32_t m = ws[k];
-        while (m) { uint32_t b = __ffs(m) - 1; m &= m - 1; slowlist[o++] = (uint16_t)((lane * 4 + k) * 32 + b); }
-    }
-    __syncwarp();
-    // restore the pre-tile value of every slow bucket (all members of a bucket carry the same `old`)
-    for (uint32_t i = lane; i < nslow; i += 32) { uint2 d = S.slowdata[slowlist[i]]; S.tab[d.x & 0xFFFFu] = (uint16_t)(d.y & 0xFFFFu); }
-    __syncwarp();
-    for (uint32_t c = 0; c < nslow; c += 32) {
-        const uint32_t i = c + lane;
-        const bool valid = i < nslow;
-        uint32_t pos = 0, hh = 0x10000u + lane, ff = 0;
-        if (valid) { pos = slowlist[i]; uint2 d = S.slowdata[pos]; hh = d.x & 0xFFFFu; ff = d.x >> 16; }
+    for (uint32_t c = 0; c < TILE_Q / 32; ++c) {
+        const uint32_t pos = c * 32 + lane;
+        const bool valid = pos < rem;
+        const uint32_t q = qs[pos];
+        const uint32_t p = hash_prod(q);
+        const uint32_t hh = valid ? prod_hash(p) : 0x10000u + lane;
+        const uint32_t ff = prod_fp(p, q);
         uint32_t cur = 0; bool touched = false;
         if (valid) { cur = S.tab[hh]; touched = cur != 0 || bit_test(S.vbit, hh); }
         const uint32_t grp = __match_any_sync(0xFFFFFFFFu, hh);
         const uint32_t lower = grp & lanemask_lt();
         const int pl = lower ? 31 - __clz(lower) : 0;
         const uint32_t fprev = __shfl_sync(0xFFFFFFFFu, ff, pl);
-        const bool hit = lower ? (fprev == ff) : (touched && cur == ff);
+        const bool hit = valid && (lower ? (fprev == ff) : (touched && cur == ff));
         const bool is_last = (grp & lanemask_gt()) == 0;
-        const bool unres_here = valid && !lower && !touched;
-        if (valid) {
-            if (hit) atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));
-            if (is_last && (lower || !hit)) {
-                S.tab[hh] = (uint16_t)ff;
-                if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-            }
+        if (valid && is_last && (lower || !hit)) {
+            S.tab[hh] = (uint16_t)ff;
+            if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
         }
-        append_unres(unres_here, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
+        const uint32_t fb = __ballot_sync(0xFFFFFFFFu, hit);
+        if (lane == 0) S.sigw[c] = fb;
+        append_unres(valid && !lower && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
         __syncwarp();
     }
 }
@@ -154,7 +139,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         for (uint32_t i = tid; i < 2048; i += FP_THREADS) { S.vbit[i] = 0; S.conf[i] = 0; }
         for (uint32_t i = tid; i < SIDE_N; i += FP_THREADS) S.side[i] = SIDE_EMPTY;
         if (tid < CLS_N) S.cls_count[tid] = 0;
-        if (tid == 0) { S.unres_count = 0; S.cls_overflow = 0; }
+        if (tid == 0) { S.unres_count = 0; S.cls_overflow = 0; S.nrec = 0; }
     }
     __syncthreads();
 
@@ -168,11 +153,12 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
     }
 
     for (uint64_t t = t_begin; t < t_end; ++t) {
-        uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT], old[FP_QPT], st[FP_QPT];
+        uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT];
         const uint64_t tile_q0 = t * TILE_Q;
         const uint32_t rem = (tile_q0 < nquads) ? (uint32_t)((nquads - tile_q0 < TILE_Q) ? (nquads - tile_q0) : TILE_Q) : 0u;
+        const uint32_t run_q0 = (uint32_t)((t - t_begin) * TILE_Q);
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) { q[j] = nxt[j]; st[j] = (pos0 + 32 * j < rem) ? ST_ACTIVE : 0u; }
+        for (int j = 0; j < FP_QPT; ++j) q[j] = nxt[j];
         {   // prefetch next tile (register double buffer; consumed one full tile later)
             const uint64_t q0 = tile_q0 + TILE_Q;
             const uint32_t nrem = (t + 1 < t_end && q0 < nquads) ? (uint32_t)((nquads - q0 < TILE_Q) ? (nquads - q0) : TILE_Q) : 0u;
@@ -180,106 +166,153 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 #pragma unroll
             for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nrem) ? ld_stream_u32(np + 32 * j) : 0u;
         }
-        if (tid == 0) S.cls_overflow = 0;  // last read before the previous S5; next written in phase D
 
-        // ---- phase A: read the pre-tile dictionary --------------------------------------------------
+        // ---- phase A: read the pre-tile dictionary; compact the missers into S.rec --------------------
+        uint32_t missmask = 0;    // bit j: my sub-row j quad missed
+        uint32_t setmask = 0;     // bit j: I raised the conflict bit of that quad's bucket (hit member gone slow)
+        {
+            uint32_t old[FP_QPT], tch = 0;
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            uint32_t p = hash_prod(q[j]);
-            h[j] = prod_hash(p);
-            f[j] = prod_fp(p, q[j]);
-            old[j] = S.tab[h[j]];
-        }
+            for (int j = 0; j < FP_QPT; ++j) {
+                const uint32_t p = hash_prod(q[j]);
+                h[j] = prod_hash(p);
+                f[j] = prod_fp(p, q[j]);
+                old[j] = S.tab[h[j]];
+            }
+            uint32_t mb[FP_QPT], tot = 0;
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            bool touched = old[j] != 0;
-            if (!touched) touched = bit_test(S.vbit, h[j]);
-            if (touched) st[j] |= ST_TOUCHED;
-            bool hit = touched && old[j] == f[j];
-            if ((st[j] & ST_ACTIVE) && !hit) st[j] |= ST_MISS;
+            for (int j = 0; j < FP_QPT; ++j) {
+                bool touched = old[j] != 0;
+                if (!touched) touched = bit_test(S.vbit, h[j]);
+                if (touched) tch |= 1u << j;
+                const bool miss = (pos0 + 32 * j < rem) && !(touched && old[j] == f[j]);
+                if (miss) missmask |= 1u << j;
+                mb[j] = __ballot_sync(0xFFFFFFFFu, miss);
+                tot += __popc(mb[j]);
+            }
+            if (tot) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&S.nrec, tot);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+                for (int j = 0; j < FP_QPT; ++j) {
+                    if (missmask & (1u << j))
+                        S.rec[base + __popc(mb[j] & lanemask_lt())] =
+                            make_uint2(h[j] | (f[j] << 16), (pos0 + 32 * j) | ((tch >> j) & 1u ? R_TOUCHED : 0u) | (old[j] << 16));
+                    base += __popc(mb[j]);
+                }
+            }
         }
-        __syncthreads();  // S1: all reads of tab/vbit precede the publishes
+        __syncthreads();  // S1: all reads of tab/vbit precede the publishes; S.nrec = number of missers
+        const uint32_t nmiss = S.nrec;  // stable until phase C appends behind it
 
         // ---- phase B: missers publish ---------------------------------------------------------------
-#pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            if (st[j] & ST_MISS) {
-                S.tab[h[j]] = (uint16_t)f[j];  // racy between different values on purpose
-                atomicMin(&S.side[h[j] & (SIDE_N - 1)], ((pos0 + 32 * j) << 16) | h[j]);
-            }
+        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+            const uint2 r = S.rec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            S.tab[hh] = (uint16_t)(r.x >> 16);  // racy between different values on purpose
+            atomicMin(&S.side[hh & (SIDE_N - 1)], ((r.y & 0xFFFu) << 16) | hh);
         }
         __syncthreads();  // S2
 
-        // ---- phase C: read back, raise conflict bits ------------------------------------------------
+        // ---- phase C: read back ----------------------------------------------------------------------
+        // hit members: the bucket still holds my value unless some misser published (its value differs from mine)
 #pragma unroll
         for (int j = 0; j < FP_QPT; ++j) {
-            if (!(st[j] & ST_ACTIVE)) continue;
             const uint32_t pos = pos0 + 32 * j;
-            const uint32_t w = S.tab[h[j]];
-            if (!(st[j] & ST_MISS)) {
-                // hit member: the bucket still holds my value unless some misser published (its value != mine)
-                if (w == f[j]) {
-                    st[j] |= ST_FLAG;
-                } else {
-                    uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
-                    if ((slot & 0xFFFFu) == h[j] && pos < (slot >> 16)) st[j] |= ST_FLAG;  // every misser of my bucket comes after me
-                    else st[j] |= ST_SLOW | ST_SETTER;
-                }
-            } else {
-                uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
-                if ((slot & 0xFFFFu) != h[j] || w != f[j]) st[j] |= ST_SLOW | ST_SETTER;  // foreign slot owner, or missers disagree
-                else {
-                    st[j] |= ST_TENT;
-                    if (slot == ((pos << 16) | h[j])) st[j] |= ST_FIRST;
+            bool ok = false;
+            if (pos < rem && !(missmask & (1u << j))) {
+                ok = S.tab[h[j]] == f[j];
+                if (!ok) {
+                    const uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
+                    if ((slot & 0xFFFFu) == h[j] && pos < (slot >> 16)) {
+                        ok = true;  // every misser of my bucket comes after me
+                    } else {
+                        // slow hit member: join the records and my class list, raise the conflict bit
+                        const uint32_t idx = atomicAdd(&S.nrec, 1u);
+                        S.rec[idx] = make_uint2(h[j] | (f[j] << 16), pos | R_TOUCHED | (f[j] << 16));
+                        const uint32_t c = h[j] >> 11;
+                        const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
+                        if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)idx; else S.cls_overflow = 1;
+                        atomicOr(&S.conf[h[j] >> 5], 1u << (h[j] & 31));
+                        setmask |= 1u << j;
+                    }
                 }
             }
-            if (st[j] & ST_SETTER) atomicOr(&S.conf[h[j] >> 5], 1u << (h[j] & 31));
+            const uint32_t fb = __ballot_sync(0xFFFFFFFFu, ok);
+            if (lane == 0) S.sigw[warp * 4 + j] = fb;
+        }
+        // missers: do all missers of my bucket agree, and who is first?
+        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+            const uint2 r = S.rec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            const uint32_t slot = S.side[hh & (SIDE_N - 1)];
+            const uint32_t w = S.tab[hh];
+            uint32_t y = r.y;
+            if ((slot & 0xFFFFu) != hh || w != (r.x >> 16)) {   // foreign slot owner, or missers disagree
+                y |= R_SLOW | R_SETTER;
+                atomicOr(&S.conf[hh >> 5], 1u << (hh & 31));
+            } else if (slot == (((r.y & 0xFFFu) << 16) | hh)) {
+                y |= R_FIRST;
+            }
+            if (y != r.y) S.rec[i].y = y;
         }
         __syncthreads();  // S3
 
-        // ---- phase D: classify; slow members publish themselves into their class list ----------------
-#pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            const uint32_t pos = pos0 + 32 * j;
-            if (st[j] & ST_TENT) {
-                if (bit_test(S.conf, h[j])) {
-                    st[j] |= ST_SLOW;
-                } else if (st[j] & ST_FIRST) {
-                    // first misser of a bucket whose missers all agree: a genuine miss (or unresolved first touch)
-                    if (!(st[j] & ST_TOUCHED)) st[j] |= ST_UNRES;
-                    if (f[j] == 0) atomicOr(&S.vbit[h[j] >> 5], 1u << (h[j] & 31));
-                } else {
-                    st[j] |= ST_FLAG;  // predecessor in the bucket is a misser with my value
-                }
-            }
-            if (st[j] & ST_MISS) S.side[h[j] & (SIDE_N - 1)] = SIDE_EMPTY;
-            if (st[j] & ST_SLOW) {
-                S.slowdata[pos] = make_uint2(h[j] | (f[j] << 16), old[j] | ((st[j] & ST_TOUCHED) ? 0x10000u : 0u));
-                const uint32_t c = h[j] >> 11;
+        // ---- phase D: missers classify ----------------------------------------------------------------
+        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+            const uint2 r = S.rec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            uint32_t y = r.y;
+            if (!(y & R_SLOW) && bit_test(S.conf, hh)) { y |= R_SLOW; S.rec[i].y = y; }
+            if (y & R_SLOW) {
+                const uint32_t c = hh >> 11;
                 const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
-                if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)pos; else S.cls_overflow = 1;
+                if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)i; else S.cls_overflow = 1;
+            } else if (!(y & R_FIRST)) {
+                const uint32_t pos = y & 0xFFFu;
+                atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));  // predecessor in the bucket is a misser with my value
             }
-            uint32_t sb = __ballot_sync(0xFFFFFFFFu, (st[j] & ST_SLOW) != 0);
-            uint32_t fb = __ballot_sync(0xFFFFFFFFu, (st[j] & ST_FLAG) != 0);
-            if (lane == 0) { S.slowmap[warp * 4 + j] = sb; S.sigw[warp * 4 + j] = fb; }
+            S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
         }
         __syncthreads();  // S4
 
-        // ---- phase F: unresolved appends, conflict-bit cleanup, slow members (warp w <- class w) -----
-        const uint32_t run_q0 = (uint32_t)((t - t_begin) * TILE_Q);
-        if (__any_sync(0xFFFFFFFFu, ((st[0] | st[1] | st[2] | st[3]) & (ST_UNRES | ST_SETTER)) != 0)) {
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j) {
-                append_unres((st[j] & ST_UNRES) != 0, run_q0 + pos0 + 32 * j, h[j], f[j], &S.unres_count, unres_run);
-                if (st[j] & ST_SETTER) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
-            }
-        }
+        // ---- phase F ------------------------------------------------------------------------------------
         if (S.cls_overflow) {
-            if (warp == 0) slow_path_sequential(S, &S.cls_list[0][0], run_q0, unres_run);
-            if (warp == 1 && lane < CLS_N) S.cls_count[lane] = 0;
+            // restore the pre-tile dictionary (only missers wrote), clear the per-tile state, walk the tile in order
+            for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+                const uint2 r = S.rec[i];
+                S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
+                if (r.y & R_SETTER) atomicAnd(&S.conf[(r.x & 0xFFFFu) >> 5], ~(1u << (r.x & 31)));
+            }
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j)
+                if (setmask & (1u << j)) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
+            if (tid < CLS_N) S.cls_count[tid] = 0;
+            __syncthreads();
+            uint32_t* qs = reinterpret_cast<uint32_t*>(S.rec);
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j) qs[pos0 + 32 * j] = q[j];
+            if (tid == 0) { S.nrec = 0; S.cls_overflow = 0; }
+            __syncthreads();
+            if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run);
         } else {
-            // In-order semantics per bucket: my predecessor is the member of my bucket with the largest smaller
-            // position; without one the pre-tile value `old` decides. The last member leaves its value behind.
+            // first missers of agreeing buckets: genuine miss or unresolved first touch; deferred vbit; conflict-bit cleanup
+            for (uint32_t base = warp * 32; base < nmiss; base += FP_THREADS) {
+                const uint32_t i = base + lane;
+                uint2 r = make_uint2(0, 0);
+                if (i < nmiss) r = S.rec[i];
+                const uint32_t hh = r.x & 0xFFFFu;
+                const bool first = (i < nmiss) && (r.y & (R_FIRST | R_SLOW)) == R_FIRST;
+                if (first && (r.x >> 16) == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                if (r.y & R_SETTER) atomicAnd(&S.conf[hh >> 5], ~(1u << (hh & 31)));
+                append_unres(first && !(r.y & R_TOUCHED), run_q0 + (r.y & 0xFFFu), hh, r.x >> 16, &S.unres_count, unres_run);
+            }
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j)
+                if (setmask & (1u << j)) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
+            // slow members, warp w <- class w. In-order semantics per bucket: my predecessor is the member of my bucket
+            // with the largest smaller position; without one the pre-tile value decides. The last member's value stays.
             const uint32_t n = S.cls_count[warp];
             const uint16_t* __restrict__ lst = S.cls_list[warp];
             for (uint32_t base = 0; base < n; base += 32) {
@@ -287,14 +320,13 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
                 const bool valid = i < n;
                 uint32_t pos = 0, hh = 0xFFFFFFFFu, ff = 0, oldv = 0; bool touched = false;
                 if (valid) {
-                    pos = lst[i];
-                    const uint2 d = S.slowdata[pos];
-                    hh = d.x & 0xFFFFu; ff = d.x >> 16; oldv = d.y & 0xFFFFu; touched = (d.y >> 16) & 1u;
+                    const uint2 d = S.rec[lst[i]];
+                    hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & 0xFFFu; touched = (d.y & R_TOUCHED) != 0; oldv = d.y >> 16;
                 }
                 int best = -1; uint32_t bestf = 0; bool later = false;
                 for (uint32_t k = 0; k < n; ++k) {
-                    const uint32_t pk = lst[k];          // broadcast reads
-                    const uint2 dk = S.slowdata[pk];
+                    const uint2 dk = S.rec[lst[k]];      // broadcast reads
+                    const uint32_t pk = dk.y & 0xFFFu;
                     if ((dk.x & 0xFFFFu) == hh) {
                         if (pk < pos && (int)pk > best) { best = (int)pk; bestf = dk.x >> 16; }
                         later |= pk > pos;
@@ -310,11 +342,12 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             }
             __syncwarp();
             if (lane == 0) S.cls_count[warp] = 0;
+            if (tid == 0) S.nrec = 0;
         }
         __syncthreads();  // S5: dictionary final for this tile, sigw final
 
         if (tid < TILE_Q / 32) sigw_g[tile_q0 / 32 + tid] = S.sigw[tid];  // workspace is sized in whole tiles
-        // (next iteration's phase D rewrites S.sigw only after three more barriers)
+        // (the next iteration rewrites S.sigw only after two more barriers)
     }
 
     // ---- export the run's last-writer table ---------------------------------------------------------

@@ -229,3 +229,41 @@ def test_decode_oracle_streams_and_vice_versa(codecs):
         assert (gpu_decode(C, enc_cpu, data.size) == data).all()
         enc_gpu = gpu_encode(C, data)
         assert (oracle.decode(alg, enc_gpu, data.size) == data).all()
+
+
+def test_sharded_stream_equals_single_call(torch_cuda, codecs):
+    """SURVEY §8e on one GPU: cut one stream into 3 shards, run phase 1 on each, fold the exported tables left to
+    right, run phase 2 with the carried-in dictionary; the concatenation must equal the oracle's single-call output."""
+    torch = torch_cuda
+    import ctypes
+    import density_b200
+    from density_b200 import sharded, synth
+    L = density_b200.load()
+    n = 3 * (1 << 21) + 515
+    data = synth.synth_text(n).numpy()
+    want = oracle.encode("chameleon", data)
+    cuts = [0, 1 << 21, (1 << 21) + (1 << 20) + 256 * 7, n]
+    encs, tables, ins = [], [], []
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for r in range(3):
+        d_in = torch.from_numpy(data[cuts[r]:cuts[r + 1]].copy()).cuda()
+        t = torch.empty(65536, dtype=torch.int32, device="cuda")
+        e = sharded.ShardedChameleonEncoder()
+        rc = L.density_b200_shard_phase1(e._h, d_in.data_ptr(), d_in.numel(), int(r == 2), t.data_ptr(), stream)
+        assert rc == 0, density_b200._lib.last_error()
+        encs.append(e); tables.append(t); ins.append(d_in)
+    gathered = torch.stack(tables)
+    pieces = []
+    for r in range(3):
+        carry = sharded.fold_tables(gathered, r) if r > 0 else None
+        d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(ins[r].numel()) + 64, dtype=torch.uint8, device="cuda")
+        d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+        d_fl = torch.zeros(1, dtype=torch.int32, device="cuda")
+        rc = L.density_b200_shard_phase2(encs[r]._h, carry.data_ptr() if carry is not None else None, d_out.data_ptr(),
+                                         d_out.numel(), d_sz.data_ptr(), d_fl.data_ptr(), stream)
+        assert rc == 0, density_b200._lib.last_error()
+        torch.cuda.synchronize()
+        assert int(d_fl.item()) == 0
+        pieces.append(d_out[:int(d_sz.item())].cpu().numpy())
+    got = np.concatenate(pieces)
+    assert got.size == want.size and (got == want).all()

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdensity_b200.so")
+SO_PATH = os.environ.get("DENSITY_B200_SO") or os.path.join(_HERE, "libdensity_b200.so")  # env override: kernel-variant experiments
 
 _c_u8p = ctypes.c_void_p
 _SIGS = {

@@ -11,7 +11,7 @@ SOURCES = ["api.cu", "chameleon_encode.cu", "scalar_codec.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",
-]
+] + os.environ.get("DENSITY_B200_NVCC_EXTRA", "").split()
 
 
 def nvcc_path():

@@ -160,6 +160,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep rank 0's stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = density_b200.load()
     C = density_b200.Chameleon

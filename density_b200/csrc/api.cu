@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 namespace dns {
 
@@ -47,8 +48,11 @@ struct DeviceCtx {
     int dev = -1;
     int num_sms = 0;
     bool ready = false;
-    cudaStream_t stream = nullptr;     // for the synchronous host-pointer entry points
-    DevBuf ws, stage_in, stage_out;
+    cudaStream_t stream = nullptr;     // for the synchronous host-pointer entry points (compute)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the pipelined host path
+    DevBuf ws, stage_in, stage_out, pipe_tables;
+    uint64_t* h_sizes = nullptr;       // pinned, PIPE_MAX_CHUNKS entries
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     uint64_t* d_size = nullptr;        // 8 B device
     uint64_t* h_size = nullptr;        // 8 B pinned
     ChamLayout layout{};
@@ -79,10 +83,13 @@ static DeviceCtx* current_ctx() {
         c->dev = dev;
         c->num_sms = prop.multiProcessorCount;
         e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) { set_error("cudaStreamCreate", e); return nullptr; }
         e = cudaMalloc(&c->d_size, 64);
         if (e != cudaSuccess) { set_error("cudaMalloc", e); return nullptr; }
         e = cudaMallocHost(&c->h_size, 64);
+        if (e == cudaSuccess) e = cudaMallocHost(&c->h_sizes, sizeof(uint64_t) * 4096);
         if (e != cudaSuccess) { set_error("cudaMallocHost", e); return nullptr; }
         c->ready = true;
     }
@@ -151,6 +158,75 @@ static int decode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
     return DENSITY_B200_OK;
 }
 
+// Host-pointer Chameleon encode, pipelined over PCIe: the input is cut into chunks that are treated as shards of one
+// bit-exact stream (same mechanism as the multi-GPU path): while chunk i+1 is still crossing PCIe, chunk i runs
+// phase 1 (flags) + phase 2 (carry-in from the chunks before it, scan, emit) and chunk i-1's output travels back.
+// Returns bytes written, 0 on error, or (size_t)-1 when the stream turned out not to be "quiet" (caller falls back
+// to the whole-buffer path with the protection-aware walk; the input is already resident in stage_in).
+constexpr size_t PIPE_CHUNK = 64u << 20;
+constexpr size_t PIPE_MIN_BYTES = 96u << 20;
+
+static size_t chameleon_encode_host_pipelined(DeviceCtx* c, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap) {
+    const size_t nchunks = (n + PIPE_CHUNK - 1) / PIPE_CHUNK;
+    if (nchunks > 4096) return (size_t)-1;
+    cudaError_t e = c->stage_in.ensure(n + 16);
+    if (e == cudaSuccess) e = c->stage_out.ensure(safe_size(ALG_CHAMELEON, n) + 16);
+    if (e == cudaSuccess) e = c->pipe_tables.ensure(2 * 65536 * sizeof(uint32_t) + (nchunks + 1) * sizeof(uint64_t) + 256);
+    ChamLayout L;
+    if (e == cudaSuccess) e = c->ws.ensure(cham_workspace_bytes(PIPE_CHUNK, c->num_sms, &L));
+    if (e != cudaSuccess) { set_error("pipeline cudaMalloc", e); return 0; }
+    c->layout = L;
+    uint32_t* d_acc = reinterpret_cast<uint32_t*>(c->pipe_tables.p);            // dictionary before the current chunk
+    uint32_t* d_tab = d_acc + 65536;                                              // last-writer table of the current chunk
+    uint64_t* d_sizes = reinterpret_cast<uint64_t*>(c->pipe_tables.p + 2 * 65536 * sizeof(uint32_t));
+    uint32_t* d_flag = reinterpret_cast<uint32_t*>(d_sizes + nchunks);
+    for (int k = 0; k < 2; ++k) if (!c->ev_h2d[k]) cudaEventCreateWithFlags(&c->ev_h2d[k], cudaEventDisableTiming);
+    uint64_t launches = 0;
+    // all H2D copies are queued up front on the copy stream; one event per chunk would be ideal, two rotating events
+    // are enough because the compute stream consumes them in order
+    std::vector<cudaEvent_t> evs(nchunks, nullptr);
+    bool ok = true;
+    for (size_t i = 0; i < nchunks && ok; ++i) {
+        const size_t off = i * PIPE_CHUNK, len = (n - off < PIPE_CHUNK) ? (n - off) : PIPE_CHUNK;
+        ok = cudaMemcpyAsync(c->stage_in.p + off, in + off, len, cudaMemcpyHostToDevice, c->h2d_stream) == cudaSuccess;
+        if (ok) ok = cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming) == cudaSuccess;
+        if (ok) ok = cudaEventRecord(evs[i], c->h2d_stream) == cudaSuccess;
+    }
+    size_t out_off = 0;
+    bool nonquiet = false;
+    e = cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), c->stream);
+    if (ok && e == cudaSuccess) e = cham_table_init(d_acc, c->stream, &launches);
+    for (size_t i = 0; i < nchunks && ok && e == cudaSuccess; ++i) {
+        const size_t off = i * PIPE_CHUNK, len = (n - off < PIPE_CHUNK) ? (n - off) : PIPE_CHUNK;
+        const uint32_t nruns = cham_pick_runs(len, c->num_sms);
+        e = cudaStreamWaitEvent(c->stream, evs[i], 0);
+        if (e == cudaSuccess) e = cham_encode_phase1(c->stage_in.p + off, len, c->ws.p, L, nruns, d_tab, c->stream, &launches);
+        if (e == cudaSuccess) e = cham_encode_phase2(c->stage_in.p + off, len, c->ws.p, L, nruns, i ? d_acc : nullptr, c->stage_out.p + out_off,
+                                                     c->stage_out.bytes - out_off, d_sizes + i, false, i != 0, c->stream, &launches);
+        if (e == cudaSuccess) e = cham_status_accumulate(c->ws.p, L, d_flag, c->stream, &launches);
+        if (e == cudaSuccess) e = cham_table_fold(d_acc, d_tab, c->stream, &launches);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_sizes + i, d_sizes + i, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_size, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // chunk i done; later H2D copies keep flowing meanwhile
+        if (e != cudaSuccess) break;
+        if (*reinterpret_cast<uint32_t*>(c->h_size) != 0) { nonquiet = true; break; }
+        const uint64_t sz = c->h_sizes[i];
+        if (sz == 0) { ok = false; set_error("pipelined encode: device reported an error"); break; }
+        if (out_off + sz > out_cap) { ok = false; set_error("output buffer too small"); break; }
+        e = cudaMemcpyAsync(out + out_off, c->stage_out.p + out_off, sz, cudaMemcpyDeviceToHost, c->d2h_stream);
+        out_off += sz;
+    }
+    g_launches += launches;
+    cudaError_t e2 = cudaStreamSynchronize(c->h2d_stream);
+    cudaError_t e3 = cudaStreamSynchronize(c->d2h_stream);
+    for (auto ev : evs) if (ev) cudaEventDestroy(ev);
+    if (e != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { set_error("pipelined encode", e != cudaSuccess ? e : (e2 != cudaSuccess ? e2 : e3)); return 0; }
+    if (!ok) return 0;
+    if (nonquiet) return (size_t)-1;
+    c->last_was_chameleon_fastpath_capable = 2;   // pipelined: quiet by construction
+    return out_off;
+}
+
 // Synchronous entry point shared by the nine reference-shaped symbols.
 static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap) {
     g_last_error.clear();
@@ -164,7 +240,14 @@ static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_
     const uint8_t* d_in = in;
     uint8_t* d_out = out;
     size_t d_cap = out_cap;
-    if (!in_dev) {
+    bool input_staged = false;
+    if (encode && alg == ALG_CHAMELEON && !in_dev && !out_dev && n >= PIPE_MIN_BYTES) {
+        const size_t r = chameleon_encode_host_pipelined(c, in, n, out, out_cap);
+        if (r != (size_t)-1) return r;
+        input_staged = true;   // not quiet: the whole input is already in stage_in; redo with the protection-aware fallback
+        d_in = c->stage_in.p;
+    }
+    if (!in_dev && !input_staged) {
         e = c->stage_in.ensure(n + 16);
         if (e != cudaSuccess) { set_error("staging cudaMalloc", e); return 0; }
         e = cudaMemcpyAsync(c->stage_in.p, in, n, cudaMemcpyHostToDevice, c->stream);
@@ -359,6 +442,7 @@ int density_b200_last_encode_was_fast(void) {
     DeviceCtx* c = current_ctx();
     if (!c) return 0;
     std::lock_guard<std::mutex> lk(c->mu);
+    if (c->last_was_chameleon_fastpath_capable == 2) return 1;
     if (!c->last_was_chameleon_fastpath_capable || !c->ws.p) return 0;
     Status st;
     if (cudaMemcpy(&st, c->ws.p + c->layout.status, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
@@ -377,6 +461,10 @@ void density_b200_shutdown(void) {
         if (c.d_size) cudaFree(c.d_size);
         if (c.h_size) cudaFreeHost(c.h_size);
         if (c.stream) cudaStreamDestroy(c.stream);
+        if (c.h2d_stream) cudaStreamDestroy(c.h2d_stream);
+        if (c.d2h_stream) cudaStreamDestroy(c.d2h_stream);
+        if (c.h_sizes) cudaFreeHost(c.h_sizes);
+        c.h2d_stream = c.d2h_stream = nullptr; c.h_sizes = nullptr; c.pipe_tables.release();
         for (auto& set : c.ev) for (auto& e : set) if (e) { cudaEventDestroy(e); e = nullptr; }
         c.d_size = nullptr; c.h_size = nullptr; c.stream = nullptr; c.ready = false;
     }

@@ -679,6 +679,9 @@ cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, co
     }
 }
 
+__global__ void cham_status_accumulate_k(const Status* __restrict__ st, uint32_t* __restrict__ flag) {
+    if (st->nonquiet || st->error) *flag = 1;
+}
 __global__ void cham_table_init_k(uint32_t* __restrict__ t) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 65536) t[i] = (i == 0) ? 0x10000u : 0u;  // stream start: bucket 0 "holds quad 0" (chameleon.rs:41,89-91)
@@ -820,6 +823,11 @@ cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
     return cudaGetLastError();
 }
 
+cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches) {
+    cham_status_accumulate_k<<<1, 1, 0, stream>>>(reinterpret_cast<const Status*>(ws + L.status), d_flag);
+    ++*launches;
+    return cudaGetLastError();
+}
 cudaError_t cham_table_init(uint32_t* d_table, cudaStream_t stream, uint64_t* launches) {
     cham_table_init_k<<<65536 / 256, 256, 0, stream>>>(d_table);
     ++*launches;

@@ -34,7 +34,8 @@ cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* 
 cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
                           uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
 
-// table helpers (sharded API)
+// table helpers (sharded API, pipelined host path)
+cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches);
 cudaError_t cham_table_init(uint32_t* d_table, cudaStream_t stream, uint64_t* launches);
 cudaError_t cham_table_fold(uint32_t* d_acc, const uint32_t* d_next, cudaStream_t stream, uint64_t* launches);
 

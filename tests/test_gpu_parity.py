@@ -267,3 +267,15 @@ def test_sharded_stream_equals_single_call(torch_cuda, codecs):
         pieces.append(d_out[:int(d_sz.item())].cpu().numpy())
     got = np.concatenate(pieces)
     assert got.size == want.size and (got == want).all()
+
+
+@pytest.mark.parametrize("kind", ["text", "mixed"])
+def test_chameleon_host_pipelined_path_bit_exact(torch_cuda, codecs, kind):
+    """>= 96 MiB host buffers take the PCIe-pipelined path (64 MiB chunks as shards of one stream); a non-quiet input
+    makes it fall back to the whole-buffer protection-aware path. Both must equal the oracle."""
+    from density_b200 import synth
+    n = 160 * (1 << 20) + 12345
+    data = (synth.synth_text(n) if kind == "text" else synth.synth_mixed(n)).numpy()
+    want = oracle.encode("chameleon", data)
+    got = gpu_encode(codecs["chameleon"], data)
+    assert got.size == want.size and (got == want).all()

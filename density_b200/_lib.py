@@ -18,6 +18,7 @@ _SIGS = {
     "density_b200_encode_device": (ctypes.c_int, [ctypes.c_int, _c_u8p, ctypes.c_size_t, _c_u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "density_b200_decode_device": (ctypes.c_int, [ctypes.c_int, _c_u8p, ctypes.c_size_t, _c_u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "density_b200_encode_device_path": (ctypes.c_int, [ctypes.c_int, _c_u8p, ctypes.c_size_t, _c_u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "density_b200_decode_device_path": (ctypes.c_int, [ctypes.c_int, _c_u8p, ctypes.c_size_t, _c_u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "density_b200_shard_create": (ctypes.c_void_p, []),
     "density_b200_shard_destroy": (None, [ctypes.c_void_p]),
     "density_b200_shard_phase1": (ctypes.c_int, [ctypes.c_void_p, _c_u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),

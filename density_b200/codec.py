@@ -148,9 +148,9 @@ def encode_device(alg, d_in, d_out, d_out_size, stream=None, path=0):
         raise EncodeError(f"density_b200_encode_device rc={rc}: {_lib.last_error()}")
 
 
-def decode_device(alg, d_in, n_in, d_out, d_out_size, stream=None):
+def decode_device(alg, d_in, n_in, d_out, d_out_size, stream=None, path=0):
     L = _lib.load()
-    rc = L.density_b200_decode_device(ALG_IDS[alg], d_in.data_ptr(), n_in, d_out.data_ptr(), d_out.numel(),
-                                      d_out_size.data_ptr(), _stream_handle(stream))
+    rc = L.density_b200_decode_device_path(ALG_IDS[alg], d_in.data_ptr(), n_in, d_out.data_ptr(), d_out.numel(),
+                                           d_out_size.data_ptr(), _stream_handle(stream), path)
     if rc != 0:
         raise DecodeError(f"density_b200_decode_device rc={rc}: {_lib.last_error()}")

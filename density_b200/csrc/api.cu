@@ -147,10 +147,26 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
     return DENSITY_B200_OK;
 }
 
+// path: 0 auto (parallel decoder with exact in-order fallback), 1 parallel only, 3 in-order kernel only
 static int decode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
-                                uint64_t* d_out_size, cudaStream_t stream) {
+                                uint64_t* d_out_size, cudaStream_t stream, int path = 0) {
     uint64_t launches = 0;
-    cudaError_t e = c->ws.ensure(scalar_workspace_bytes(alg));
+    cudaError_t e;
+    const bool parallel_ok = alg == ALG_CHAMELEON && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 1) && !(reinterpret_cast<uintptr_t>(d_out) & 3);
+    if (parallel_ok) {
+        // parallel decoder; the exact in-order kernel is queued behind it and only runs when the stream has copy-mode blocks
+        const size_t pw = (cham_decode_workspace_bytes(n, c->num_sms) + 255) & ~(size_t)255;
+        e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg));
+        if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+        uint32_t* d_nonquiet = reinterpret_cast<uint32_t*>(c->ws.p + pw);
+        e = cham_decode_parallel(d_in, n, d_out, cap, c->ws.p, c->num_sms, d_out_size, d_nonquiet, stream, &launches);
+        if (e == cudaSuccess && path != 1)
+            e = scalar_decode(alg, d_in, n, d_out, cap, c->ws.p + pw + 256, d_out_size, stream, &launches, d_nonquiet);
+        g_launches += launches;
+        if (e != cudaSuccess) { set_error("decode launch", e); return DENSITY_B200_ECUDA; }
+        return DENSITY_B200_OK;
+    }
+    e = c->ws.ensure(scalar_workspace_bytes(alg));
     if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
     e = scalar_decode(alg, d_in, n, d_out, cap, c->ws.p, d_out_size, stream, &launches);
     g_launches += launches;
@@ -310,7 +326,7 @@ static int device_entry(bool encode, int alg, const uint8_t* d_in, size_t n, uin
         return DENSITY_B200_OK;
     }
     return encode ? encode_device_locked(c, alg, d_in, n, d_out, cap, d_out_size, s, path)
-                  : decode_device_locked(c, alg, d_in, n, d_out, cap, d_out_size, s);
+                  : decode_device_locked(c, alg, d_in, n, d_out, cap, d_out_size, s, path);
 }
 
 int density_b200_encode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size, void* stream) {
@@ -323,6 +339,11 @@ int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint
                                     void* stream, int path) {
     if (path < 0 || path > 3) { set_error("bad path"); return DENSITY_B200_EARG; }
     return device_entry(true, alg, d_in, n, d_out, cap, d_out_size, stream, path);
+}
+int density_b200_decode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                                    void* stream, int path) {
+    if (path != 0 && path != 1 && path != 3) { set_error("bad path"); return DENSITY_B200_EARG; }
+    return device_entry(false, alg, d_in, n, d_out, cap, d_out_size, stream, path);
 }
 
 // ---- sharded Chameleon encode ------------------------------------------------------------------------

@@ -1,0 +1,559 @@
+// chameleon_decode.cu — parallel Chameleon decode for sm_100a.
+//
+// Replaces /root/reference/src/algorithms/chameleon/chameleon.rs:55-68,103-135 (decode_plain / decode_map / decode_unit /
+// decode_partial_unit) driven by /root/reference/src/codec/codec.rs:82-126 (Codec::decode), bit-exactly.
+//
+// The reference decoder has three serial chains: block boundaries (block b+1 starts where block b's
+// payload ends; nothing in the stream says where), the protection automaton, and the dictionary (a MAP quad reads the most
+// recent PLAIN quad with that hash). This file breaks them as follows.
+//
+//  1. Boundaries.  A full encoded block is 8 + 256 - 2*popc(sig) bytes. The stream is cut into 16 KiB chunks; for each
+//     chunk and each of the 132 possible (even) entry offsets in its first 264 bytes, `dec_chunk_walk` walks the chunk in
+//     shared memory and records where that walk leaves the chunk and how many blocks it saw. Composing these 132-entry maps
+//     (per group of 64 chunks, then over the groups, then back down) yields every chunk's true entry point and block
+//     index; `dec_block_offsets` re-walks each chunk from its true entry and writes one offset per block.
+//  2. Protection.  `dec_quiet_check`: if no two consecutive blocks are incompressible (>= 256 bytes consumed, codec.rs:98)
+//     the automaton never leaves its initial state and no block is in copy mode (same argument as the encoder). Otherwise
+//     the caller falls back to the exact in-order kernel (scalar_codec.cu).
+//  3. Dictionary.  `cham_decode_pass`: one persistent CTA per contiguous run of blocks, the run's dictionary in shared
+//     memory as 16-bit fingerprints (common.cuh). Per tile of 4096 quads: PLAIN quads (~8 %) are the writers, MAP quads the
+//     readers; barrier-phased optimistic protocol — A readers read / B writers publish / C readers re-read; unchanged means
+//     no writer touched the bucket in this tile / D the few readers whose bucket was written resolve exactly (all writers
+//     later than me -> pre-tile value; writers agree and one precedes me -> that value; else search the tile's writer list).
+//     A reader whose bucket has not been written in this run yet cannot know the carried-in dictionary: it is recorded
+//     and patched afterwards from the per-run carry-in tables (same machinery as the encoder).
+//  4. Tail.  The last < 264 bytes of the stream (codec.rs:102-123: per-unit bounds checks, partial units, 1-3 raw bytes) are
+//     decoded by one thread with the reference's literal control flow, starting from the folded dictionary.
+#include "common.cuh"
+#include "encode_internal.cuh"
+
+namespace dns {
+namespace chamdec {
+
+constexpr int CH = 16384;            // chunk of compressed stream
+constexpr int NCAND = 132;           // even entry offsets 0..262
+constexpr int GROUP = 64;            // chunks per composition group
+constexpr uint32_t TERM = 0xFFu;     // exit code: the walk reached the tail region / end of stream
+
+struct DecStatus {
+    unsigned long long out_bytes;
+    unsigned long long main_blocks;      // blocks decoded by the parallel main loop (codec.rs:88-100)
+    unsigned long long tail_off;         // stream offset where the tail loop starts
+    unsigned int nonquiet, error;
+    unsigned int last_main_inc, pad;
+};
+
+__device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
+
+// ---- 1a. candidate walks -----------------------------------------------------------------------------------------------
+// res[chunk][cand] = exit_idx | nblocks << 8 | term_rel << 16   (exit_idx == TERM: walk ended inside this chunk at relative
+// offset term_rel because fewer than 264 bytes remain: that is where codec.rs's tail loop takes over)
+__global__ void __launch_bounds__(160) dec_chunk_walk(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, uint32_t* __restrict__ res) {
+    __shared__ __align__(16) uint8_t s[CH + 288];
+    const uint32_t c = blockIdx.x;
+    const uint64_t base = (uint64_t)c * CH;
+    for (uint32_t i = threadIdx.x * 2; i < CH + 288; i += blockDim.x * 2) {
+        const uint64_t g = base + i;
+        *reinterpret_cast<uint16_t*>(s + i) = (g + 2 <= n) ? *reinterpret_cast<const uint16_t*>(in + g) : (uint16_t)((g < n) ? in[g] : 0);
+    }
+    __syncthreads();
+    const uint32_t cand = threadIdx.x;
+    if (cand >= NCAND) return;
+    uint32_t off = cand * 2, nb = 0, exitc = TERM, term = 0;
+    while (true) {
+        if (off >= (uint32_t)CH) { exitc = (off - CH) >> 1; break; }
+        if (base + off + 264 > n) { term = off; break; }
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(s + off);
+        const uint32_t hits = __popc((uint32_t)p[0] | ((uint32_t)p[1] << 16)) + __popc((uint32_t)p[2] | ((uint32_t)p[3] << 16));
+        off += 264 - 2 * hits;
+        ++nb;
+    }
+    res[(size_t)c * NCAND + cand] = exitc | (nb << 8) | (term << 16);
+    (void)nchunks;
+}
+
+// ---- 1b. compose the maps of GROUP consecutive chunks ----------------------------------------------------------------------
+// gres[g][cand] = {exit_idx (or TERM), blocks, term_chunk, term_rel}
+__global__ void dec_group_compose(const uint32_t* __restrict__ res, uint32_t nchunks, uint4* __restrict__ gres) {
+    const uint32_t g = blockIdx.x, cand = threadIdx.x;
+    if (cand >= NCAND) return;
+    uint32_t idx = cand, blocks = 0, tchunk = 0, trel = 0;
+    const uint32_t c0 = g * GROUP, c1 = min(nchunks, c0 + GROUP);
+    for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t r = res[(size_t)c * NCAND + idx];
+        blocks += (r >> 8) & 0xFFu;
+        idx = r & 0xFFu;
+        if (idx == TERM) { tchunk = c; trel = r >> 16; break; }
+    }
+    gres[(size_t)g * NCAND + cand] = make_uint4(idx, blocks, tchunk, trel);
+}
+
+// ---- 1c. walk the groups from the stream start ---------------------------------------------------------------------------
+__global__ void dec_top_walk(const uint4* __restrict__ gres, uint32_t ngroups, uint64_t n, uint32_t* __restrict__ g_entry,
+                             uint64_t* __restrict__ g_blockbase, DecStatus* __restrict__ st) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t idx = 0; uint64_t blocks = 0;
+    bool done = false;
+    for (uint32_t g = 0; g < ngroups; ++g) {
+        g_entry[g] = done ? TERM : idx;
+        g_blockbase[g] = blocks;
+        if (done) continue;
+        const uint4 r = gres[(size_t)g * NCAND + idx];
+        blocks += r.y;
+        idx = r.x;
+        if (idx == TERM) { done = true; st->tail_off = (unsigned long long)r.z * CH + r.w; }
+    }
+    if (!done) st->tail_off = n;  // cannot happen for n > 0 (the last chunk always terminates); keeps the tail kernel safe
+    st->main_blocks = blocks;
+}
+
+// ---- 1d. per chunk: true entry + block index -----------------------------------------------------------------------------
+__global__ void dec_chunk_entries(const uint32_t* __restrict__ res, uint32_t nchunks, const uint32_t* __restrict__ g_entry,
+                                  const uint64_t* __restrict__ g_blockbase, uint32_t ngroups, uint32_t* __restrict__ c_entry,
+                                  uint64_t* __restrict__ c_blockbase) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    uint32_t idx = g_entry[g]; uint64_t blocks = g_blockbase[g];
+    const uint32_t c0 = g * GROUP, c1 = min(nchunks, c0 + GROUP);
+    for (uint32_t c = c0; c < c1; ++c) {
+        c_entry[c] = idx; c_blockbase[c] = blocks;
+        if (idx == TERM) continue;
+        const uint32_t r = res[(size_t)c * NCAND + idx];
+        blocks += (r >> 8) & 0xFFu;
+        idx = r & 0xFFu;
+    }
+}
+
+// ---- 1e. one offset per block ------------------------------------------------------------------------------------------------
+__global__ void dec_block_offsets(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, const uint32_t* __restrict__ c_entry,
+                                  const uint64_t* __restrict__ c_blockbase, uint64_t* __restrict__ blk_off) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const uint32_t e = c_entry[c];
+    if (e == TERM) return;
+    const uint64_t base = (uint64_t)c * CH;
+    uint64_t b = c_blockbase[c];
+    uint32_t off = e * 2;
+    while (off < (uint32_t)CH && base + off + 264 <= n) {
+        const uint8_t* p = in + base + off;
+        blk_off[b++] = base + off;
+        const uint32_t hits = __popc(ldu16(p) | (ldu16(p + 2) << 16)) + __popc(ldu16(p + 4) | (ldu16(p + 6) << 16));
+        off += 264 - 2 * hits;
+    }
+}
+
+// ---- 2. quiet check + capacity check -------------------------------------------------------------------------------------------
+__global__ void dec_quiet_check(const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, DecStatus* __restrict__ st, uint64_t cap) {
+    const uint64_t nb = st->main_blocks;
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0 && nb * 256 > cap) st->error = 2;  // DENSITY_B200_ECAPACITY
+    if (b >= nb) return;
+    const uint8_t* p = in + blk_off[b];
+    const uint32_t hits = __popc(ldu16(p) | (ldu16(p + 2) << 16)) + __popc(ldu16(p + 4) | (ldu16(p + 6) << 16));
+    const bool inc = hits <= 4;  // consumed = 8 + 256 - 2*hits >= 256 (codec.rs:98)
+    if (b == nb - 1) st->last_main_inc = inc ? 1u : 0u;
+    if (inc && b > 0) {
+        const uint8_t* q = in + blk_off[b - 1];
+        const uint32_t h2 = __popc(ldu16(q) | (ldu16(q + 2) << 16)) + __popc(ldu16(q + 4) | (ldu16(q + 6) << 16));
+        if (h2 <= 4) atomicOr(&st->nonquiet, 1u);
+    }
+}
+
+// ---- 3. decode pass ---------------------------------------------------------------------------------------------------------
+constexpr int DP_THREADS = 1024;
+constexpr int DP_QPT = 4;
+constexpr int TILE_Q = DP_THREADS * DP_QPT;   // 4096 quads = 64 blocks
+constexpr int SIDE_N = 4096;
+constexpr uint32_t SIDE_EMPTY = 0xFFFFFFFFu;
+constexpr int SUS_CAP = 2048;      // suspect readers per tile (readers whose bucket is written in this tile); more -> in-order fallback
+
+// writer record: x = hash | fp << 16, y = pos(12) | agree-flag etc.   suspect reader record: x = hash | w << 16, y = pos | touched << 12 | fa << 16
+constexpr uint32_t W_CONF = 1u << 12;
+constexpr uint32_t S_TOUCHED = 1u << 12;
+
+struct DecSmem {
+    uint16_t tab[65536];
+    uint32_t vbit[2048];
+    uint32_t conf[2048];          // per-tile: writers of the bucket disagree
+    uint32_t wbit[2048];          // per-tile: bucket has a writer in this tile
+    uint32_t side[SIDE_N];        // per-tile min over writers of (pos << 16 | hash)
+    uint2 wrec[TILE_Q];           // writers (plain quads) of the tile
+    uint2 srec[SUS_CAP];          // suspect readers
+    unsigned long long boff[64];  // stream offset of each block of the tile
+    uint32_t bsig[128];           // signature halves
+    uint32_t nw, ns, overflow;
+};
+static_assert(sizeof(DecSmem) <= 227 * 1024, "decode pass shared memory");
+
+__device__ __forceinline__ bool bit_test(const uint32_t* bm, uint32_t i) { return (bm[i >> 5] >> (i & 31)) & 1u; }
+
+// WONLY = true: "writer pass" — only the PLAIN quads are looked at; produces each run's last-writer table so that the
+// carry-in dictionary of every run is known before the real decode pass starts (a MAP quad cannot tell what its bucket
+// held at the start of the run). WONLY = false: the decode pass proper, dictionary preloaded from `carry`.
+template <bool WONLY>
+__global__ void __launch_bounds__(DP_THREADS, 1)
+cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, DecStatus* st,
+                 uint32_t nruns, uint32_t* __restrict__ out /* quads */, const uint32_t* __restrict__ carry,
+                 uint32_t* __restrict__ final_tab) {
+    if (st->nonquiet || st->error) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecSmem& S = *reinterpret_cast<DecSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t run = blockIdx.x;
+    const uint64_t nblocks = st->main_blocks;
+    const uint64_t ntiles = (nblocks + 63) / 64;
+    const uint64_t t_begin = (uint64_t)run * ntiles / nruns, t_end = (uint64_t)(run + 1) * ntiles / nruns;
+
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* t4 = reinterpret_cast<uint4*>(S.tab);
+        for (uint32_t i = tid; i < 65536 * 2 / 16; i += DP_THREADS) t4[i] = z;
+        for (uint32_t i = tid; i < 2048; i += DP_THREADS) { S.vbit[i] = 0; S.conf[i] = 0; S.wbit[i] = 0; }
+        if (!WONLY) {
+            __syncthreads();
+            const uint32_t* __restrict__ cr = carry + (size_t)run * 65536;   // dictionary before this run
+            for (uint32_t i = tid; i < 65536; i += DP_THREADS) {
+                const uint32_t c = cr[i];
+                if (c & 0x10000u) {
+                    S.tab[i] = (uint16_t)c;
+                    if ((c & 0xFFFFu) == 0) atomicOr(&S.vbit[i >> 5], 1u << (i & 31));
+                }
+            }
+        }
+        for (uint32_t i = tid; i < SIDE_N; i += DP_THREADS) S.side[i] = SIDE_EMPTY;
+        if (tid == 0) { S.nw = 0; S.ns = 0; S.overflow = 0; }
+    }
+    __syncthreads();
+
+    for (uint64_t t = t_begin; t < t_end; ++t) {
+        const uint64_t b0 = t * 64;
+        const uint32_t nb_tile = (uint32_t)((nblocks - b0 < 64) ? (nblocks - b0) : 64);
+        // ---- stage block offsets + signatures -----------------------------------------------------------------------
+        if (tid < 64) {
+            unsigned long long o = 0; uint32_t lo = 0, hi = 0;
+            if (tid < nb_tile) {
+                o = blk_off[b0 + tid];
+                const uint8_t* p = in + o;
+                lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
+            }
+            S.boff[tid] = o; S.bsig[2 * tid] = lo; S.bsig[2 * tid + 1] = hi;
+        }
+        __syncthreads();  // S0
+
+        // ---- phase A: fetch my quads; writers compact themselves; readers read the pre-tile dictionary ----------------
+        uint32_t val[DP_QPT];       // PLAIN: the quad; MAP: hash from the stream
+        uint32_t fa[DP_QPT];        // readers: pre-tile fingerprint
+        uint32_t kind = 0;          // per sub-row: bit j = active, bit 4+j = writer, bit 8+j = reader bucket touched pre-tile
+        uint32_t wb[DP_QPT], wtot = 0;
+#pragma unroll
+        for (int j = 0; j < DP_QPT; ++j) {
+            const uint32_t bl = warp * 2 + (j >> 1);
+            const uint32_t k = (j & 1) * 32 + lane;
+            bool active = bl < nb_tile, writer = false;
+            val[j] = 0; fa[j] = 0;
+            if (active) {
+                const uint32_t lo = S.bsig[2 * bl], hi = S.bsig[2 * bl + 1];
+                const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
+                const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
+                const uint8_t* p = in + S.boff[bl] + 8 + 4 * k - 2 * before;
+                if (flag) {
+                    if (!WONLY) {
+                        val[j] = ldu16(p);                              // decode_map reads the 16-bit hash (chameleon.rs:64)
+                        fa[j] = S.tab[val[j]];
+                        if (fa[j] != 0 || bit_test(S.vbit, val[j])) kind |= 1u << (8 + j);
+                    }
+                } else {
+                    val[j] = ldu16(p) | (ldu16(p + 2) << 16);           // decode_plain reads the quad (chameleon.rs:56)
+                    writer = true;
+                }
+                kind |= 1u << j;
+            }
+            if (writer) kind |= 1u << (4 + j);
+            wb[j] = __ballot_sync(0xFFFFFFFFu, writer);
+            wtot += __popc(wb[j]);
+        }
+        if (wtot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&S.nw, wtot);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+            for (int j = 0; j < DP_QPT; ++j) {
+                if (kind & (1u << (4 + j))) {
+                    const uint32_t p = hash_prod(val[j]);
+                    S.wrec[base + __popc(wb[j] & lanemask_lt())] = make_uint2(prod_hash(p) | (prod_fp(p, val[j]) << 16), warp * 128 + j * 32 + lane);
+                }
+                base += __popc(wb[j]);
+            }
+        }
+        __syncthreads();  // S1: readers have read tab; writer list complete
+        const uint32_t nw = S.nw;
+
+        // ---- phase B: writers publish ----------------------------------------------------------------------------------
+#pragma unroll 1
+        for (uint32_t i = tid; i < nw; i += DP_THREADS) {
+            const uint2 r = S.wrec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            S.tab[hh] = (uint16_t)(r.x >> 16);
+            atomicMin(&S.side[hh & (SIDE_N - 1)], ((r.y & 0xFFFu) << 16) | hh);
+            atomicOr(&S.wbit[hh >> 5], 1u << (hh & 31));
+        }
+        __syncthreads();  // S2
+
+        // ---- phase C: readers re-read; writers check agreement ---------------------------------------------------------
+        const uint64_t q0 = b0 * 64;   // first output quad of the tile
+        if (!WONLY) {
+#pragma unroll
+            for (int j = 0; j < DP_QPT; ++j) {
+                const uint32_t pos = warp * 128 + j * 32 + lane;
+                const bool active = kind & (1u << j), writer = kind & (1u << (4 + j));
+                const bool touched = kind & (1u << (8 + j));
+                bool suspect = false;
+                if (active) {
+                    if (writer) {
+                        out[q0 + pos] = val[j];
+                    } else if (!bit_test(S.wbit, val[j])) {
+                        // no PLAIN quad of this tile falls into my bucket: the pre-tile dictionary decides (empty -> 0, chameleon.rs:41)
+                        out[q0 + pos] = touched ? quad_from_hf(val[j], fa[j]) : 0u;
+                    } else {
+                        suspect = true;
+                    }
+                }
+                const uint32_t sm = __ballot_sync(0xFFFFFFFFu, suspect);
+                if (sm) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&S.ns, (uint32_t)__popc(sm));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (suspect) {
+                        const uint32_t e = base + __popc(sm & lanemask_lt());
+                        if (e < SUS_CAP) S.srec[e] = make_uint2(val[j], pos | (touched ? S_TOUCHED : 0u) | (fa[j] << 16));
+                        else S.overflow = 1;
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (uint32_t i = tid; i < nw; i += DP_THREADS) {
+            const uint2 r = S.wrec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            const uint32_t slot = S.side[hh & (SIDE_N - 1)];
+            if ((slot & 0xFFFFu) != hh || S.tab[hh] != (r.x >> 16)) {   // foreign slot owner, or the writers of my bucket disagree
+                S.wrec[i].y = r.y | W_CONF;
+                atomicOr(&S.conf[hh >> 5], 1u << (hh & 31));
+            }
+        }
+        __syncthreads();  // S3
+        const uint32_t ns = S.ns < (uint32_t)SUS_CAP ? S.ns : (uint32_t)SUS_CAP;
+
+        // ---- phase D: suspect readers resolve; writers of disagreeing buckets leave the last value ----------------------
+        if (!WONLY) {
+#pragma unroll 1
+            for (uint32_t i = tid; i < ns; i += DP_THREADS) {
+                const uint2 r = S.srec[i];
+                const uint32_t hs = r.x & 0xFFFFu, pos = r.y & 0xFFFu;
+                uint32_t fval = r.y >> 16; bool have = (r.y & S_TOUCHED) != 0;   // pre-tile value
+                const uint32_t slot = S.side[hs & (SIDE_N - 1)];
+                if ((slot & 0xFFFFu) == hs && pos < (slot >> 16)) {
+                    // every writer of my bucket comes after me: pre-tile value
+                } else if ((slot & 0xFFFFu) == hs && !bit_test(S.conf, hs)) {
+                    fval = S.tab[hs]; have = true;                               // the writers agree and the first one precedes me
+                } else {
+                    int best = -1;                                               // search the tile's writers for my predecessor
+                    for (uint32_t k = 0; k < nw; ++k) {
+                        const uint2 d = S.wrec[k];
+                        const int pk = (int)(d.y & 0xFFFu);
+                        if ((d.x & 0xFFFFu) == hs && pk < (int)pos && pk > best) { best = pk; fval = d.x >> 16; have = true; }
+                    }
+                }
+                out[q0 + pos] = have ? quad_from_hf(hs, fval) : 0u;
+            }
+        }
+#pragma unroll 1
+        for (uint32_t i = tid; i < nw; i += DP_THREADS) {
+            const uint2 r = S.wrec[i];
+            const uint32_t hh = r.x & 0xFFFFu, ff = r.x >> 16, pos = r.y & 0xFFFu;
+            if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+            if (r.y & W_CONF) {
+                bool later = false;
+                for (uint32_t k = 0; k < nw; ++k) {
+                    const uint2 d = S.wrec[k];
+                    later |= (d.x & 0xFFFFu) == hh && (d.y & 0xFFFu) > pos;
+                }
+                if (!later) S.tab[hh] = (uint16_t)ff;               // the last writer of the bucket wins (chameleon.rs:59)
+            }
+        }
+        __syncthreads();  // S4: all readers of conf/side/lists done
+#pragma unroll 1
+        for (uint32_t i = tid; i < nw; i += DP_THREADS) {
+            const uint2 r = S.wrec[i];
+            if (r.y & W_CONF) atomicAnd(&S.conf[(r.x & 0xFFFFu) >> 5], ~(1u << (r.x & 31)));
+            atomicAnd(&S.wbit[(r.x & 0xFFFFu) >> 5], ~(1u << (r.x & 31)));
+            S.side[(r.x & 0xFFFFu) & (SIDE_N - 1)] = SIDE_EMPTY;
+        }
+        if (tid == 0) { S.nw = 0; S.ns = 0; }
+        // (the next tile's S0 orders these against its phase A)
+    }
+
+    for (uint32_t i = tid; i < 65536; i += DP_THREADS) {
+        uint32_t v = S.tab[i];
+        uint32_t tch = (v != 0 || bit_test(S.vbit, i)) ? 0x10000u : 0u;
+        final_tab[(size_t)run * 65536 + i] = v | tch;
+    }
+    if (tid == 0 && S.overflow) atomicOr(&st->nonquiet, 2u);  // suspect list overflow: fall back to the in-order kernel
+}
+
+// carry-in fold for decode: initial dictionary is all zero values (chameleon.rs:41): nothing touched.
+__global__ void dec_carry_scan(const uint32_t* __restrict__ final_tab, uint32_t nruns, uint32_t* __restrict__ carry, uint32_t* __restrict__ dict_out) {
+    uint32_t hb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hb >= 65536) return;
+    uint32_t c = 0;
+    for (uint32_t r = 0; r < nruns; ++r) {
+        carry[(size_t)r * 65536 + hb] = c;
+        uint32_t v = final_tab[(size_t)r * 65536 + hb];
+        if (v & 0x10000u) c = v;
+    }
+    dict_out[hb] = (c & 0x10000u) ? quad_from_hf(hb, c & 0xFFFFu) : 0u;   // full-width dictionary for the tail loop
+}
+
+// ---- 4. tail loop (codec.rs:102-123), one thread, literal control flow ---------------------------------------------------
+__global__ void dec_tail(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, uint32_t* __restrict__ dict,
+                         DecStatus* __restrict__ st, uint64_t* __restrict__ d_out_size) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (st->nonquiet) return;                 // the caller's in-order fallback produces the result
+    if (st->error) { st->out_bytes = 0; if (d_out_size) *d_out_size = 0; return; }
+    uint64_t idx = st->tail_off, oidx = st->main_blocks * 256;
+    Protection ps; ps.init();
+    ps.counter = st->main_blocks;             // quiet so far: penalty 0, start 1 (protection_state.rs:9-16,38-43)
+    ps.previous_incompressible = st->last_main_inc;
+    bool bad = false, overflow = false;
+    auto emit = [&](uint32_t q) {
+        if (oidx + 4 > cap) { overflow = true; return; }
+        out[oidx] = (uint8_t)q; out[oidx + 1] = (uint8_t)(q >> 8); out[oidx + 2] = (uint8_t)(q >> 16); out[oidx + 3] = (uint8_t)(q >> 24);
+        oidx += 4;
+    };
+    while (!bad && !overflow && n - idx > 0) {
+        if (ps.revert_to_copy()) {
+            const uint64_t rem = n - idx;
+            const uint64_t len = rem > 256 ? 256 : rem;
+            if (oidx + len > cap) { overflow = true; break; }
+            for (uint64_t i = 0; i < len; ++i) out[oidx + i] = in[idx + i];
+            oidx += len; idx += len;
+            if (rem <= 256) break;
+            ps.decay();
+        } else {
+            const uint64_t mark = idx;
+            if (n - idx < 8) { bad = true; break; }
+            uint64_t sig = 0;
+            for (int i = 0; i < 8; ++i) sig |= (uint64_t)in[idx + i] << (8 * i);
+            idx += 8;
+            bool end = false;
+            for (int u = 0; u < 32 && !end && !bad && !overflow; ++u) {        // 32 units of 2 quads (chameleon.rs:143)
+                const bool checked = (n - idx) < 8;
+                for (int k = 0; k < 2 && !end; ++k) {
+                    const uint32_t fl = (uint32_t)(sig & 1); sig >>= 1;
+                    if (checked && fl == 0) {                                    // decode_partial_unit, chameleon.rs:119-129
+                        const uint64_t rem = n - idx;
+                        if (rem == 0) { end = true; break; }
+                        if (rem < 4) {
+                            if (oidx + rem > cap) { overflow = true; end = true; break; }
+                            for (uint64_t i = 0; i < rem; ++i) out[oidx++] = in[idx++];
+                            end = true; break;
+                        }
+                    }
+                    uint32_t q;
+                    if (fl) {
+                        if (n - idx < 2) { bad = true; break; }
+                        q = dict[in[idx] | (in[idx + 1] << 8)]; idx += 2;
+                    } else {
+                        if (n - idx < 4) { bad = true; break; }
+                        q = in[idx] | (in[idx + 1] << 8) | (in[idx + 2] << 16) | ((uint32_t)in[idx + 3] << 24); idx += 4;
+                        dict[prod_hash(hash_prod(q))] = q;
+                    }
+                    emit(q);
+                }
+            }
+            if (end) break;
+            ps.update(idx - mark >= 256);
+        }
+    }
+    uint64_t res = oidx;
+    if (bad) { st->error = 3; res = 0; }
+    else if (overflow) { st->error = 2; res = 0; }
+    st->out_bytes = res;
+    if (d_out_size) *d_out_size = res;
+}
+
+}  // namespace chamdec
+
+using namespace chamdec;
+
+struct ChamDecLayout { size_t status, res, gres, g_entry, g_blockbase, c_entry, c_blockbase, blk_off, final_tab, carry, dict, total; };
+
+static size_t dec_layout(size_t nbytes, int nruns_max, ChamDecLayout* L) {
+    const uint64_t nchunks = (nbytes + CH - 1) / CH;
+    const uint64_t ngroups = (nchunks + GROUP - 1) / GROUP;
+    const uint64_t maxblocks = nbytes / 136 + 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    L->status = take(sizeof(DecStatus));
+    L->res = take(nchunks * NCAND * sizeof(uint32_t));
+    L->gres = take(ngroups * NCAND * sizeof(uint4));
+    L->g_entry = take(ngroups * sizeof(uint32_t));
+    L->g_blockbase = take(ngroups * sizeof(uint64_t));
+    L->c_entry = take(nchunks * sizeof(uint32_t));
+    L->c_blockbase = take(nchunks * sizeof(uint64_t));
+    L->blk_off = take(maxblocks * sizeof(uint64_t));
+    L->final_tab = take((size_t)nruns_max * 65536 * sizeof(uint32_t));
+    L->carry = take((size_t)nruns_max * 65536 * sizeof(uint32_t));
+    L->dict = take(65536 * sizeof(uint32_t));
+    L->total = off;
+    return off;
+}
+
+size_t cham_decode_workspace_bytes(size_t nbytes, int nruns_max) { ChamDecLayout L; return dec_layout(nbytes, nruns_max, &L); }
+
+// Enqueues the parallel decode. On return (after the stream drains) *d_nonquiet != 0 means the caller must run the exact
+// in-order kernel instead (copy-mode blocks present, or a pathological tile); d_out_size is only written when it is 0.
+cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, int num_sms,
+                                 uint64_t* d_out_size, uint32_t* d_nonquiet, cudaStream_t stream, uint64_t* launches) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e0 = cudaFuncSetAttribute(cham_decode_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+        if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(cham_decode_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+        if (e0 != cudaSuccess) return e0;
+        attr_done = true;
+    }
+    ChamDecLayout L; dec_layout(nbytes, num_sms, &L);
+    DecStatus* st = reinterpret_cast<DecStatus*>(ws + L.status);
+    cudaError_t e = cudaMemsetAsync(st, 0, sizeof(DecStatus), stream);
+    if (e != cudaSuccess) return e;
+    const uint32_t nchunks = (uint32_t)((nbytes + CH - 1) / CH);
+    const uint32_t ngroups = (nchunks + GROUP - 1) / GROUP;
+    uint32_t* res = reinterpret_cast<uint32_t*>(ws + L.res);
+    uint4* gres = reinterpret_cast<uint4*>(ws + L.gres);
+    uint32_t* g_entry = reinterpret_cast<uint32_t*>(ws + L.g_entry);
+    uint64_t* g_bb = reinterpret_cast<uint64_t*>(ws + L.g_blockbase);
+    uint32_t* c_entry = reinterpret_cast<uint32_t*>(ws + L.c_entry);
+    uint64_t* c_bb = reinterpret_cast<uint64_t*>(ws + L.c_blockbase);
+    uint64_t* blk_off = reinterpret_cast<uint64_t*>(ws + L.blk_off);
+    dec_chunk_walk<<<nchunks, 160, 0, stream>>>(d_in, nbytes, nchunks, res); ++*launches;
+    dec_group_compose<<<ngroups, 160, 0, stream>>>(res, nchunks, gres); ++*launches;
+    dec_top_walk<<<1, 32, 0, stream>>>(gres, ngroups, nbytes, g_entry, g_bb, st); ++*launches;
+    dec_chunk_entries<<<(ngroups + 127) / 128, 128, 0, stream>>>(res, nchunks, g_entry, g_bb, ngroups, c_entry, c_bb); ++*launches;
+    dec_block_offsets<<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off); ++*launches;
+    const uint64_t maxblocks = nbytes / 136 + 2;
+    dec_quiet_check<<<(unsigned)((maxblocks + 255) / 256), 256, 0, stream>>>(d_in, blk_off, st, cap); ++*launches;
+    // run count from an upper bound of the block count (the kernel reads the real one from the status block)
+    uint64_t tiles_ub = (maxblocks + 63) / 64;
+    uint32_t nruns = (uint32_t)(tiles_ub / 16); if (nruns < 1) nruns = 1; if (nruns > (uint32_t)num_sms) nruns = num_sms;
+    uint32_t* final_tab = reinterpret_cast<uint32_t*>(ws + L.final_tab);
+    uint32_t* carry = reinterpret_cast<uint32_t*>(ws + L.carry);
+    cham_decode_pass<true><<<nruns, DP_THREADS, sizeof(DecSmem), stream>>>(d_in, blk_off, st, nruns, nullptr, nullptr, final_tab); ++*launches;
+    dec_carry_scan<<<65536 / 256, 256, 0, stream>>>(final_tab, nruns, carry, reinterpret_cast<uint32_t*>(ws + L.dict)); ++*launches;
+    cham_decode_pass<false><<<nruns, DP_THREADS, sizeof(DecSmem), stream>>>(d_in, blk_off, st, nruns, reinterpret_cast<uint32_t*>(d_out), carry, final_tab); ++*launches;
+    dec_tail<<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, reinterpret_cast<uint32_t*>(ws + L.dict), st, d_out_size); ++*launches;
+    e = cudaMemcpyAsync(d_nonquiet, &st->nonquiet, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace dns

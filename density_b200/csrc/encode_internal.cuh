@@ -23,16 +23,16 @@ cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8
                                        size_t cap, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
 
 // chameleon_decode.cu
-size_t cham_decode_workspace_bytes();
-cudaError_t cham_decode(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, uint64_t* d_out_size,
-                        cudaStream_t stream, uint64_t* launches);
+size_t cham_decode_workspace_bytes(size_t nbytes, int nruns_max);
+cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, int num_sms,
+                                 uint64_t* d_out_size, uint32_t* d_nonquiet, cudaStream_t stream, uint64_t* launches);
 
 // scalar_codec.cu (Cheetah / Lion, in-order)
 size_t scalar_workspace_bytes(int alg);
 cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
                           uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
 cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if = nullptr);
 
 // table helpers (sharded API, pipelined host path)
 cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches);

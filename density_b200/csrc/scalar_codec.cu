@@ -177,8 +177,9 @@ struct Dec {
 
 template <int ALG>
 __global__ void decode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, Tables T,
-                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size) {
+                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (run_if && *run_if == 0) return;   // the parallel decoder already produced the result
     constexpr uint32_t B = ALG == ALG_CHAMELEON ? 256 : ALG == ALG_CHEETAH ? 128 : 64;
     constexpr uint32_t SB = ALG == ALG_LION ? 6 : 8;
     constexpr uint32_t UNIT = ALG == ALG_CHAMELEON ? 8 : 4;
@@ -264,15 +265,15 @@ cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* 
 }
 
 cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches) {
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if) {
     cudaError_t e = cudaMemsetAsync(ws, 0, scalar_workspace_bytes(alg), stream);
     if (e != cudaSuccess) return e;
     scalar::Tables T = carve(alg, ws);
     Status* st = reinterpret_cast<Status*>(ws);
     switch (alg) {
-    case ALG_CHAMELEON: scalar::decode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size); break;
-    case ALG_CHEETAH:   scalar::decode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size); break;
-    default:            scalar::decode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size); break;
+    case ALG_CHAMELEON: scalar::decode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
+    case ALG_CHEETAH:   scalar::decode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
+    default:            scalar::decode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
     }
     ++*launches;
     return cudaGetLastError();

@@ -82,6 +82,10 @@ DENSITY_B200_API int density_b200_encode_device(int alg, const uint8_t* d_in, si
    2 = exact in-order protection-aware walk only, 3 = scalar reference kernel. */
 DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                     uint64_t* d_out_size, void* stream, int path);
+/* Decode counterpart: path 0 = auto (parallel Chameleon decoder, exact in-order kernel when the stream has copy-mode
+   blocks), 1 = parallel decoder only (size 0 if it had to give up), 3 = in-order kernel only. */
+DENSITY_B200_API int density_b200_decode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                    uint64_t* d_out_size, void* stream, int path);
 /* Same contract for decode; `cap` must be >= the original length. */
 DENSITY_B200_API int density_b200_decode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                uint64_t* d_out_size, void* stream);

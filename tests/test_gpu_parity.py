@@ -279,3 +279,43 @@ def test_chameleon_host_pipelined_path_bit_exact(torch_cuda, codecs, kind):
     want = oracle.encode("chameleon", data)
     got = gpu_encode(codecs["chameleon"], data)
     assert got.size == want.size and (got == want).all()
+
+
+@pytest.mark.parametrize("path", [0, 1, 3])
+@pytest.mark.parametrize("nbytes", [5, 263, 264, 300, 4096, 16 * 1024 + 4, 70001, 1 << 20, (1 << 22) + 777, 24 * (1 << 20) + 3])
+def test_chameleon_decode_paths_on_text(torch_cuda, codecs, path, nbytes):
+    """path 0 auto, 1 parallel decoder only (boundary chase + tile protocol + in-order tail), 3 in-order kernel: identical."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    if path == 3 and nbytes > (1 << 22) + 777:
+        pytest.skip("in-order kernel is slow")
+    data = synth.synth_text(nbytes).numpy()
+    enc = oracle.encode("chameleon", data)          # a stream produced by the reference algorithm on the CPU
+    d_enc = torch.from_numpy(enc).cuda()
+    d_out = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.decode_device("chameleon", d_enc, enc.size, d_out, d_sz, path=path)
+    torch.cuda.synchronize()
+    assert int(d_sz.item()) == nbytes
+    assert (d_out[:nbytes].cpu().numpy() == data).all()
+
+
+@pytest.mark.parametrize("kind", ["random", "mixed", "low", "zeros"])
+def test_chameleon_decode_copy_mode_streams_fall_back_exactly(codecs, kind):
+    C = codecs["chameleon"]
+    data = payload(kind, 3 * (1 << 20) + 5, seed=5)
+    enc = oracle.encode("chameleon", data)
+    dec = gpu_decode(C, enc, data.size)
+    assert dec.size == data.size and (dec == data).all()
+
+
+def test_chameleon_decode_adversarial_same_bucket(torch_cuda, codecs):
+    """writers (plain quads) of ONE bucket interleaved with readers of that bucket inside every tile."""
+    q1, q2 = _same_bucket_pair()
+    block = np.array([q1, q1, q2, q2, q2, q1] * 6 + [0] * 28, dtype=np.uint32)
+    data = np.tile(block, 2500).view(np.uint8)[: 2500 * 256 - 1]
+    enc, copied = oracle.encode("chameleon", data, return_copied=True)
+    assert copied == 0
+    dec = gpu_decode(codecs["chameleon"], enc, data.size)
+    assert dec.size == data.size and (dec == data).all()

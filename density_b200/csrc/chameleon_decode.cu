@@ -179,8 +179,8 @@ struct DecSmem {
     uint32_t side[SIDE_N];        // per-tile min over writers of (pos << 16 | hash)
     uint2 wrec[TILE_Q];           // writers (plain quads) of the tile
     uint2 srec[SUS_CAP];          // suspect readers
-    unsigned long long boff[64];  // stream offset of each block of the tile
-    uint32_t bsig[128];           // signature halves
+    unsigned long long boff[2][64];  // stream offset of each block of the tile (double buffered: next tile staged early)
+    uint32_t bsig[2][128];           // signature halves
     uint32_t nw, ns, overflow;
 };
 static_assert(sizeof(DecSmem) <= 227 * 1024, "decode pass shared memory");
@@ -190,6 +190,40 @@ __device__ __forceinline__ bool bit_test(const uint32_t* bm, uint32_t i) { retur
 // WONLY = true: "writer pass" — only the PLAIN quads are looked at; produces each run's last-writer table so that the
 // carry-in dictionary of every run is known before the real decode pass starts (a MAP quad cannot tell what its bucket
 // held at the start of the run). WONLY = false: the decode pass proper, dictionary preloaded from `carry`.
+// Stage block offsets + signatures of the tile starting at block b0 into buffer `buf` (first 64 threads).
+__device__ __forceinline__ void stage_tile(DecSmem& S, int buf, const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off,
+                                           uint64_t b0, uint64_t nblocks) {
+    const uint32_t tid = threadIdx.x;
+    if (tid < 64) {
+        unsigned long long o = 0; uint32_t lo = 0, hi = 0;
+        if (b0 + tid < nblocks) {
+            o = blk_off[b0 + tid];
+            const uint8_t* p = in + o;
+            lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
+        }
+        S.boff[buf][tid] = o; S.bsig[buf][2 * tid] = lo; S.bsig[buf][2 * tid + 1] = hi;
+    }
+}
+// Issue the payload loads of my DP_QPT quads of the tile staged in `buf`: MAP -> 16-bit hash, PLAIN -> the quad.
+template <bool WONLY>
+__device__ __forceinline__ void fetch_payload(const DecSmem& S, int buf, const uint8_t* __restrict__ in, uint32_t nb_tile, uint32_t (&v)[DP_QPT]) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < DP_QPT; ++j) {
+        const uint32_t bl = warp * 2 + (j >> 1);
+        const uint32_t k = (j & 1) * 32 + lane;
+        v[j] = 0;
+        if (bl < nb_tile) {
+            const uint32_t lo = S.bsig[buf][2 * bl], hi = S.bsig[buf][2 * bl + 1];
+            const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
+            const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
+            const uint8_t* p = in + S.boff[buf][bl] + 8 + 4 * k - 2 * before;
+            if (flag) { if (!WONLY) v[j] = ldu16(p); }                       // decode_map reads the 16-bit hash (chameleon.rs:64)
+            else v[j] = ldu16(p) | (ldu16(p + 2) << 16);                     // decode_plain reads the quad (chameleon.rs:56)
+        }
+    }
+}
+
 template <bool WONLY>
 __global__ void __launch_bounds__(DP_THREADS, 1)
 cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, DecStatus* st,
@@ -225,22 +259,20 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
     }
     __syncthreads();
 
+    // prologue: stage the first tile and issue its payload loads
+    uint32_t nval[DP_QPT];
+    if (t_begin < t_end) stage_tile(S, 0, in, blk_off, t_begin * 64, nblocks);
+    __syncthreads();
+    if (t_begin < t_end) fetch_payload<WONLY>(S, 0, in, (uint32_t)((nblocks - t_begin * 64 < 64) ? (nblocks - t_begin * 64) : 64), nval);
+
     for (uint64_t t = t_begin; t < t_end; ++t) {
         const uint64_t b0 = t * 64;
         const uint32_t nb_tile = (uint32_t)((nblocks - b0 < 64) ? (nblocks - b0) : 64);
-        // ---- stage block offsets + signatures -----------------------------------------------------------------------
-        if (tid < 64) {
-            unsigned long long o = 0; uint32_t lo = 0, hi = 0;
-            if (tid < nb_tile) {
-                o = blk_off[b0 + tid];
-                const uint8_t* p = in + o;
-                lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
-            }
-            S.boff[tid] = o; S.bsig[2 * tid] = lo; S.bsig[2 * tid + 1] = hi;
-        }
-        __syncthreads();  // S0
+        const int cur = (int)((t - t_begin) & 1);
+        // stage the NEXT tile's offsets + signatures now; they become visible at S1 and feed the payload prefetch
+        if (t + 1 < t_end) stage_tile(S, cur ^ 1, in, blk_off, b0 + 64, nblocks);
 
-        // ---- phase A: fetch my quads; writers compact themselves; readers read the pre-tile dictionary ----------------
+        // ---- phase A: my quads (prefetched); writers compact themselves; readers read the pre-tile dictionary ----------
         uint32_t val[DP_QPT];       // PLAIN: the quad; MAP: hash from the stream
         uint32_t fa[DP_QPT];        // readers: pre-tile fingerprint
         uint32_t kind = 0;          // per sub-row: bit j = active, bit 4+j = writer, bit 8+j = reader bucket touched pre-tile
@@ -248,22 +280,16 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
 #pragma unroll
         for (int j = 0; j < DP_QPT; ++j) {
             const uint32_t bl = warp * 2 + (j >> 1);
-            const uint32_t k = (j & 1) * 32 + lane;
             bool active = bl < nb_tile, writer = false;
-            val[j] = 0; fa[j] = 0;
+            val[j] = nval[j]; fa[j] = 0;
             if (active) {
-                const uint32_t lo = S.bsig[2 * bl], hi = S.bsig[2 * bl + 1];
-                const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
-                const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
-                const uint8_t* p = in + S.boff[bl] + 8 + 4 * k - 2 * before;
+                const uint32_t flag = (S.bsig[cur][2 * bl + (j & 1)] >> lane) & 1u;
                 if (flag) {
                     if (!WONLY) {
-                        val[j] = ldu16(p);                              // decode_map reads the 16-bit hash (chameleon.rs:64)
                         fa[j] = S.tab[val[j]];
                         if (fa[j] != 0 || bit_test(S.vbit, val[j])) kind |= 1u << (8 + j);
                     }
                 } else {
-                    val[j] = ldu16(p) | (ldu16(p + 2) << 16);           // decode_plain reads the quad (chameleon.rs:56)
                     writer = true;
                 }
                 kind |= 1u << j;
@@ -285,8 +311,10 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
                 base += __popc(wb[j]);
             }
         }
-        __syncthreads();  // S1: readers have read tab; writer list complete
+        __syncthreads();  // S1: readers have read tab; writer list complete; next tile's signatures staged
         const uint32_t nw = S.nw;
+        if (t + 1 < t_end)   // payload of the next tile: in flight during phases B-D
+            fetch_payload<WONLY>(S, cur ^ 1, in, (uint32_t)((nblocks - (b0 + 64) < 64) ? (nblocks - (b0 + 64)) : 64), nval);
 
         // ---- phase B: writers publish ----------------------------------------------------------------------------------
 #pragma unroll 1
@@ -347,38 +375,60 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
         // ---- phase D: suspect readers resolve; writers of disagreeing buckets leave the last value ----------------------
         if (!WONLY) {
 #pragma unroll 1
-            for (uint32_t i = tid; i < ns; i += DP_THREADS) {
-                const uint2 r = S.srec[i];
-                const uint32_t hs = r.x & 0xFFFFu, pos = r.y & 0xFFFu;
-                uint32_t fval = r.y >> 16; bool have = (r.y & S_TOUCHED) != 0;   // pre-tile value
-                const uint32_t slot = S.side[hs & (SIDE_N - 1)];
-                if ((slot & 0xFFFFu) == hs && pos < (slot >> 16)) {
-                    // every writer of my bucket comes after me: pre-tile value
-                } else if ((slot & 0xFFFFu) == hs && !bit_test(S.conf, hs)) {
-                    fval = S.tab[hs]; have = true;                               // the writers agree and the first one precedes me
-                } else {
-                    int best = -1;                                               // search the tile's writers for my predecessor
-                    for (uint32_t k = 0; k < nw; ++k) {
-                        const uint2 d = S.wrec[k];
-                        const int pk = (int)(d.y & 0xFFFu);
-                        if ((d.x & 0xFFFFu) == hs && pk < (int)pos && pk > best) { best = pk; fval = d.x >> 16; have = true; }
+            for (uint32_t base = warp * 32; base < ns; base += DP_THREADS) {
+                const uint32_t i = base + lane;
+                uint32_t hs = 0, pos = 0, fval = 0; bool have = false, search = false;
+                if (i < ns) {
+                    const uint2 r = S.srec[i];
+                    hs = r.x & 0xFFFFu; pos = r.y & 0xFFFu;
+                    fval = r.y >> 16; have = (r.y & S_TOUCHED) != 0;             // pre-tile value
+                    const uint32_t slot = S.side[hs & (SIDE_N - 1)];
+                    if ((slot & 0xFFFFu) == hs && pos < (slot >> 16)) {
+                        // every writer of my bucket comes after me: pre-tile value
+                    } else if ((slot & 0xFFFFu) == hs && !bit_test(S.conf, hs)) {
+                        fval = S.tab[hs]; have = true;                           // the writers agree and the first one precedes me
+                    } else {
+                        search = true;                                           // disagreeing writers, or the side slot belongs to another bucket
                     }
                 }
-                out[q0 + pos] = have ? quad_from_hf(hs, fval) : 0u;
+                // warp-cooperative search of the tile's writer list for the predecessor of each lane that needs it
+                uint32_t todo = __ballot_sync(0xFFFFFFFFu, search);
+                while (todo) {
+                    const int src = __ffs(todo) - 1; todo &= todo - 1;
+                    const uint32_t shs = __shfl_sync(0xFFFFFFFFu, hs, src), spos = __shfl_sync(0xFFFFFFFFu, pos, src);
+                    uint32_t key = 0;
+                    for (uint32_t k = lane; k < nw; k += 32) {
+                        const uint2 d = S.wrec[k];
+                        const uint32_t pk = d.y & 0xFFFu;
+                        if ((d.x & 0xFFFFu) == shs && pk < spos) key = max(key, ((pk + 1) << 16) | (d.x >> 16));
+                    }
+                    key = __reduce_max_sync(0xFFFFFFFFu, key);
+                    if ((int)lane == src && key) { fval = key & 0xFFFFu; have = true; }
+                }
+                if (i < ns) out[q0 + pos] = have ? quad_from_hf(hs, fval) : 0u;
             }
         }
 #pragma unroll 1
-        for (uint32_t i = tid; i < nw; i += DP_THREADS) {
-            const uint2 r = S.wrec[i];
-            const uint32_t hh = r.x & 0xFFFFu, ff = r.x >> 16, pos = r.y & 0xFFFu;
-            if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-            if (r.y & W_CONF) {
+        for (uint32_t base = warp * 32; base < nw; base += DP_THREADS) {
+            const uint32_t i = base + lane;
+            uint32_t hh = 0x10000u, ff = 0, pos = 0; bool confw = false;
+            if (i < nw) {
+                const uint2 r = S.wrec[i];
+                hh = r.x & 0xFFFFu; ff = r.x >> 16; pos = r.y & 0xFFFu; confw = (r.y & W_CONF) != 0;
+                if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+            }
+            // writers of disagreeing buckets: the last one (largest position) leaves its value (chameleon.rs:59)
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, confw);
+            while (todo) {
+                const int src = __ffs(todo) - 1; todo &= todo - 1;
+                const uint32_t shh = __shfl_sync(0xFFFFFFFFu, hh, src), spos = __shfl_sync(0xFFFFFFFFu, pos, src);
                 bool later = false;
-                for (uint32_t k = 0; k < nw; ++k) {
+                for (uint32_t k = lane; k < nw; k += 32) {
                     const uint2 d = S.wrec[k];
-                    later |= (d.x & 0xFFFFu) == hh && (d.y & 0xFFFu) > pos;
+                    later |= (d.x & 0xFFFFu) == shh && (d.y & 0xFFFu) > spos;
                 }
-                if (!later) S.tab[hh] = (uint16_t)ff;               // the last writer of the bucket wins (chameleon.rs:59)
+                later = __any_sync(0xFFFFFFFFu, later);
+                if ((int)lane == src && !later) S.tab[hh] = (uint16_t)ff;
             }
         }
         __syncthreads();  // S4: all readers of conf/side/lists done
@@ -390,7 +440,7 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
             S.side[(r.x & 0xFFFFu) & (SIDE_N - 1)] = SIDE_EMPTY;
         }
         if (tid == 0) { S.nw = 0; S.ns = 0; }
-        // (the next tile's S0 orders these against its phase A)
+        __syncthreads();  // S5: counters reset before the next tile's phase A
     }
 
     for (uint32_t i = tid; i < 65536; i += DP_THREADS) {

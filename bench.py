@@ -264,6 +264,26 @@ def run_ours(args):
                "steps": k, "api": ("chameleon_encode(host ptr, n, host ptr, cap): C ABI, pinned host buffers, synchronous" if world == 1 else
                                    "ShardedChameleonEncoder.encode with pinned host buffers: H2D + phase1 + all_gather + phase2 + D2H per step")}
 
+    # ---- extra (not the headline metric): Chameleon decode of the stream just produced, device-resident, N=1 only -------
+    extra = None
+    if world == 1:
+        d_dec = torch.empty(n, dtype=torch.uint8, device=dev)
+        d_dsz = torch.zeros(1, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            density_b200.decode_device("chameleon", d_out, out_bytes, d_dec, d_dsz)
+        torch.cuda.synchronize()
+        assert int(d_dsz.item()) == n and torch.equal(d_dec, d_in), "decode(encode(x)) != x"
+        k = max(3, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            density_b200.decode_device("chameleon", d_out, out_bytes, d_dec, d_dsz)
+        e1.record(); torch.cuda.synchronize()
+        dms = e0.elapsed_time(e1) / k
+        extra = {"chameleon_decode_GBps": n / (dms * 1e-3) / 1e9, "decode_ms": dms, "round_trip_verified": True,
+                 "note": "uncompressed bytes / time, same convention as the reference's decompress bench (benches/density.rs:48)"}
+        del d_dec
+
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -307,6 +327,8 @@ def run_ours(args):
                             "frac": (ach / peak_gbs) if ach else None, "traffic": None, "peak_source": peak_src,
                             "step_algorithmic": {"bytes": n + out_bytes, "achieved": step_alg, "frac": step_alg / peak_gbs},
                             "input_rate_frac": value / peak_gbs, "kernels": kernels}
+    if extra:
+        line["extra"] = extra
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))

@@ -87,11 +87,11 @@ __device__ __forceinline__ void append_unres(bool pred, uint32_t qidx_in_run, ui
 // In-order walk of one whole tile by one warp, from the (restored) pre-tile dictionary. Fallback for tiles whose
 // class lists overflow (adversarial inputs: hundreds of interleaving quads in a handful of buckets).
 __device__ __noinline__ void tile_in_order(FlagSmem& S, const uint32_t* qs, uint32_t rem, uint32_t run_q0,
-                                           uint2* __restrict__ unres_run) {
+                                           uint2* __restrict__ unres_run, const uint8_t* __restrict__ cm_tile) {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t c = 0; c < TILE_Q / 32; ++c) {
         const uint32_t pos = c * 32 + lane;
-        const bool valid = pos < rem;
+        const bool valid = pos < rem && !(cm_tile && cm_tile[pos >> 6]);   // copy-mode blocks never touch the dictionary (codec.rs:35-37)
         const uint32_t q = qs[pos];
         const uint32_t p = hash_prod(q);
         const uint32_t hh = valid ? prod_hash(p) : 0x10000u + lane;
@@ -120,8 +120,11 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
                uint32_t* __restrict__ sigw_g,        // 2 x u32 per block (low half first)
                uint2* __restrict__ unres,            // nruns x 65536
                uint32_t* __restrict__ unres_count,   // nruns
-               uint32_t* __restrict__ final_tab)     // nruns x 65536: touched << 16 | fp
+               uint32_t* __restrict__ final_tab,     // nruns x 65536: touched << 16 | fp
+               const uint8_t* __restrict__ copymap,  // optional: 1 byte per block, non-zero = copy-mode block (skipped)
+               const Status* __restrict__ gate)      // optional: run only while the protection iteration is still open
 {
+    if (gate && !(gate->nonquiet && !gate->converged)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FlagSmem& S = *reinterpret_cast<FlagSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -167,6 +170,14 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nrem) ? ld_stream_u32(np + 32 * j) : 0u;
         }
 
+        uint32_t actmask = 0;     // bit j: my sub-row j quad exists and its block is not in copy mode
+        {
+            uint32_t cp = 0;      // bit 0/1: block 2*warp / 2*warp+1 of this tile is a copy-mode block
+            if (copymap) cp = (copymap[t * 64 + warp * 2] ? 1u : 0u) | (copymap[t * 64 + warp * 2 + 1] ? 2u : 0u);
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j)
+                if (pos0 + 32 * j < rem && !((cp >> (j >> 1)) & 1u)) actmask |= 1u << j;
+        }
         // ---- phase A: read the pre-tile dictionary; compact the missers into S.rec --------------------
         uint32_t missmask = 0;    // bit j: my sub-row j quad missed
         uint32_t setmask = 0;     // bit j: I raised the conflict bit of that quad's bucket (hit member gone slow)
@@ -185,7 +196,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
                 bool touched = old[j] != 0;
                 if (!touched) touched = bit_test(S.vbit, h[j]);
                 if (touched) tch |= 1u << j;
-                const bool miss = (pos0 + 32 * j < rem) && !(touched && old[j] == f[j]);
+                const bool miss = ((actmask >> j) & 1u) && !(touched && old[j] == f[j]);
                 if (miss) missmask |= 1u << j;
                 mb[j] = __ballot_sync(0xFFFFFFFFu, miss);
                 tot += __popc(mb[j]);
@@ -221,7 +232,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         for (int j = 0; j < FP_QPT; ++j) {
             const uint32_t pos = pos0 + 32 * j;
             bool ok = false;
-            if (pos < rem && !(missmask & (1u << j))) {
+            if (((actmask >> j) & 1u) && !(missmask & (1u << j))) {
                 ok = S.tab[h[j]] == f[j];
                 if (!ok) {
                     const uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
@@ -295,7 +306,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             for (int j = 0; j < FP_QPT; ++j) qs[pos0 + 32 * j] = q[j];
             if (tid == 0) { S.nrec = 0; S.cls_overflow = 0; }
             __syncthreads();
-            if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run);
+            if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run, copymap ? copymap + t * 64 : nullptr);
         } else {
             // first missers of agreeing buckets: genuine miss or unresolved first touch; deferred vbit; conflict-bit cleanup
             for (uint32_t base = warp * 32; base < nmiss; base += FP_THREADS) {
@@ -363,8 +374,12 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 // carry-in tables: carry[r] = state of the dictionary before run r (as touched<<16 | fp)
 // `init` = state before run 0 (NULL: the stream start, where only bucket 0 "holds quad 0").
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool gate_open(const Status* g) { return !g || (g->nonquiet && !g->converged); }
+
 __global__ void cham_carry_scan(const uint32_t* __restrict__ final_tab, const uint32_t* __restrict__ init, int init_untouched,
-                                uint32_t nruns, uint32_t* __restrict__ carry, uint32_t* __restrict__ table_out) {
+                                uint32_t nruns, uint32_t* __restrict__ carry, uint32_t* __restrict__ table_out,
+                                const Status* __restrict__ gate = nullptr) {
+    if (!gate_open(gate)) return;
     uint32_t hb = blockIdx.x * blockDim.x + threadIdx.x;
     if (hb >= 65536) return;
     uint32_t c = init ? init[hb] : ((hb == 0 && !init_untouched) ? 0x10000u : 0u);
@@ -378,7 +393,8 @@ __global__ void cham_carry_scan(const uint32_t* __restrict__ final_tab, const ui
 
 __global__ void cham_resolve(const uint2* __restrict__ unres, const uint32_t* __restrict__ unres_count,
                              const uint32_t* __restrict__ carry, uint32_t tiles_total, uint32_t nruns,
-                             uint32_t* __restrict__ sigw_g) {
+                             uint32_t* __restrict__ sigw_g, const Status* __restrict__ gate = nullptr) {
+    if (!gate_open(gate)) return;
     const uint32_t run = blockIdx.y;
     const uint32_t n = unres_count[run];
     const uint64_t run_q0 = ((uint64_t)run * tiles_total / nruns) * TILE_Q;
@@ -405,7 +421,7 @@ struct ProtSmem {
 __global__ void __launch_bounds__(1024, 1)
 cham_protected_pass(const uint32_t* __restrict__ in, uint64_t nbytes, const Status* __restrict__ status, int only_if_nonquiet,
                     uint32_t* __restrict__ sigw_g, uint8_t* __restrict__ copymap) {
-    if (only_if_nonquiet && status->nonquiet == 0) return;
+    if (only_if_nonquiet && !(status->nonquiet && !status->converged)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ProtSmem& S = *reinterpret_cast<ProtSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -470,6 +486,152 @@ cham_protected_pass(const uint32_t* __restrict__ in, uint64_t nbytes, const Stat
         const uint32_t out_sz = 8 + 4 * nq - 2 * hits + tailb;
         ps.update(out_sz >= 256);  // codec.rs:68
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Parallel evaluation of the protection automaton (codec/protection_state.rs:18-47) over the block sequence.
+//
+// The copy map M (which blocks are in copy mode) is the fixed point of  M -> automaton(incompressible bits of the blocks
+// that M leaves encoded, computed with M's copy-mode blocks hidden from the dictionary).  Iteration: M0 = nothing copied
+// (the plain fast path), M(k+1) = automaton(flags(M(k))); when M(k+1) == M(k) the flags computed under M(k) are the
+// reference's (induction over the block index: agreeing up to block b means the same dictionary and the same automaton
+// state before b). The automaton itself is evaluated per segment of PSEG blocks from the canonical state
+// (penalty 0, start 1, previous_incompressible false) in parallel; the seams are then settled by relaxation rounds (prot_iterate) and
+// re-evaluates only the segments whose true incoming state differs (inside / right after incompressible regions).
+// ------------------------------------------------------------------------------------------------------
+constexpr int PSEG = 256;
+
+// inc[b] = "block b, when encoded, is incompressible" (8 + 256 - 2*hits >= 256, codec.rs:68), refreshed after every flag pass for
+// the blocks that pass encoded; blocks hidden by the copy map keep their last known value (from a pass in which they were
+// encoded), which is what makes the iteration converge in 1-2 rounds: the bit hardly depends on the dictionary details.
+__device__ __forceinline__ uint32_t prot_pack(const Protection& ps) { return ps.copy_penalty | (ps.copy_penalty_start << 8) | (ps.previous_incompressible << 16); }
+// Walk the blocks [b0, b1) from state `ps`; writes the copy map and leaves the outgoing state in `ps`.
+__device__ __forceinline__ void prot_walk(Protection& ps, const uint8_t* __restrict__ inc, uint64_t b0, uint64_t b1, uint8_t* __restrict__ cm) {
+    for (uint64_t b = b0; b < b1; ++b) {
+        if (ps.revert_to_copy()) { cm[b] = 1; ps.decay(); }
+        else { cm[b] = 0; ps.update(__ldcg(&inc[b]) != 0); }
+    }
+}
+// One launch per fixed-point round does the whole automaton step on a persistent grid with software grid barriers:
+//   refresh the incompressible bits -> chaotic relaxation over the segments (segment s is re-evaluated whenever the outgoing
+//   state of segment s-1 differs from the incoming state it was last evaluated with; a chain of L consecutive segments with
+//   non-canonical seams settles after L rounds) -> in-order fix-up by one CTA if PROT_ROUNDS rounds were not enough
+//   -> compare the new copy map with the one the flags were computed under -> converged / commit.
+constexpr int PROT_ROUNDS = 48;
+constexpr int PI_THREADS = 256;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nctas, unsigned int& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned int target = (epoch + 1) * nctas;
+        while (atomicAdd(counter, 0u) < target) { __nanosleep(64); }
+        __threadfence();
+    }
+    ++epoch;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PI_THREADS)
+prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* __restrict__ st, int it,
+             uint8_t* __restrict__ inc, uint8_t* __restrict__ cm_old, uint8_t* __restrict__ cm_new,
+             uint32_t* __restrict__ in_state, uint32_t* __restrict__ out_state) {
+    if (!gate_open(st)) return;                       // uniform over the grid: read before anybody modifies `converged`
+    __shared__ uint32_t s_state[1024], s_in[1024];
+    __shared__ uint8_t s_inc[PSEG], s_cm[PSEG];
+    __shared__ uint32_t s_cur, s_redo;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t gtid = (uint64_t)blockIdx.x * PI_THREADS + tid, gsz = (uint64_t)gridDim.x * PI_THREADS;
+    unsigned int epoch = 0;
+    unsigned int* bar = &st->barrier[it & 7];
+
+    // (1) incompressible bits of the blocks that were encoded in the pass just finished
+    for (uint64_t b = gtid; b < nblocks; b += gsz)
+        if (!(it && cm_old[b])) inc[b] = (nbytes - b * 256 >= 256) && (__popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]) <= 4);
+    if (gtid == 0) { st->relax_changed[0] = 0; st->relax_changed[1] = 0; st->iter_changed = 0; }
+    grid_barrier(bar, gridDim.x, epoch);
+
+    // (2) relaxation rounds
+    bool settled = false;
+    for (int round = 0; round < PROT_ROUNDS; ++round) {
+        for (uint64_t s = gtid; s < nseg; s += gsz) {
+            const uint32_t new_in = (s && round) ? __ldcg(&out_state[s - 1]) : (1u << 8);   // L2 read: written by other SMs during this kernel
+            if (round > 0 && new_in == in_state[s]) continue;
+            Protection ps;
+            ps.copy_penalty = new_in & 0xFFu; ps.copy_penalty_start = (new_in >> 8) & 0xFFu; ps.previous_incompressible = (new_in >> 16) & 1u;
+            ps.counter = s * PSEG;
+            const uint64_t b1 = ((s + 1) * PSEG < nblocks) ? (s + 1) * PSEG : nblocks;
+            prot_walk(ps, inc, s * PSEG, b1, cm_new);
+            in_state[s] = new_in;
+            out_state[s] = prot_pack(ps);
+            if (round > 0) st->relax_changed[round & 1] = 1;
+        }
+        grid_barrier(bar, gridDim.x, epoch);
+        if (round > 0) {
+            const bool changed = *((volatile unsigned int*)&st->relax_changed[round & 1]) != 0;
+            if (!changed) { settled = true; break; }
+        }
+        if (gtid == 0) st->relax_changed[(round + 1) & 1] = 0;      // the flag of the next round (nobody reads it before the next barrier)
+        grid_barrier(bar, gridDim.x, epoch);
+    }
+
+    // (3) pathologically long incompressible stretches: finish in order (one CTA; a stored result stands when it was computed
+    //     from the true incoming state)
+    if (!settled) {
+        if (blockIdx.x == 0) {
+            if (tid == 0) s_cur = 1u << 8;
+            for (uint32_t s0 = 0; s0 < nseg; s0 += 1024) {
+                __syncthreads();
+                for (uint32_t i = tid; i < 1024 && s0 + i < nseg; i += PI_THREADS) { s_state[i] = __ldcg(&out_state[s0 + i]); s_in[i] = __ldcg(&in_state[s0 + i]); }
+                __syncthreads();
+                const uint32_t cnt = (nseg - s0 < 1024u) ? (nseg - s0) : 1024u;
+                uint32_t i = 0;
+                while (i < cnt) {
+                    if (tid == 0) {
+                        uint32_t cur = s_cur;
+                        while (i < cnt && cur == s_in[i]) { cur = s_state[i]; ++i; }
+                        s_cur = cur;
+                        s_redo = (i < cnt) ? i : 0xFFFFFFFFu;
+                    }
+                    __syncthreads();
+                    const uint32_t r = s_redo;
+                    if (r == 0xFFFFFFFFu) break;
+                    const uint64_t b0 = (uint64_t)(s0 + r) * PSEG;
+                    const uint32_t nb = (uint32_t)((nblocks - b0 < (uint64_t)PSEG) ? (nblocks - b0) : PSEG);
+                    if (tid < nb) s_inc[tid] = __ldcg(&inc[b0 + tid]);
+                    __syncthreads();
+                    if (tid == 0) {
+                        Protection ps; const uint32_t c = s_cur;
+                        ps.copy_penalty = c & 0xFFu; ps.copy_penalty_start = (c >> 8) & 0xFFu; ps.previous_incompressible = (c >> 16) & 1u; ps.counter = b0;
+                        for (uint32_t k = 0; k < nb; ++k) {
+                            if (ps.revert_to_copy()) { s_cm[k] = 1; ps.decay(); }
+                            else { s_cm[k] = 0; ps.update(s_inc[k] != 0); }
+                        }
+                        s_cur = prot_pack(ps);
+                    }
+                    __syncthreads();
+                    if (tid < nb) cm_new[b0 + tid] = s_cm[tid];
+                    i = r + 1;
+                    __syncthreads();
+                }
+            }
+        }
+        grid_barrier(bar, gridDim.x, epoch);
+    }
+
+    // (4) fixed point reached?
+    {
+        bool diff = false;
+        for (uint64_t b = gtid; b < nblocks; b += gsz) diff |= __ldcg(&cm_new[b]) != (it ? cm_old[b] : 0);
+        if (diff) atomicOr(&st->iter_changed, 1u);
+    }
+    grid_barrier(bar, gridDim.x, epoch);
+    const bool converged = *((volatile unsigned int*)&st->iter_changed) == 0;
+    if (!converged || it == 0)
+        for (uint64_t b = gtid; b < nblocks; b += gsz) cm_old[b] = __ldcg(&cm_new[b]);
+    grid_barrier(bar, gridDim.x, epoch);
+    if (gtid == 0 && converged) st->converged = 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -707,6 +869,9 @@ size_t cham_workspace_bytes(size_t nbytes, int nruns_max, ChamLayout* L) {
     L->status = take(sizeof(Status));
     L->sigw = take((ntiles * 64 * 2 + 64) * sizeof(uint32_t));
     L->copymap = take(ntiles * 64 + 64);
+    L->copymap2 = take(ntiles * 64 + 64);
+    L->seg_state = take((2 * (ntiles * 64 / PSEG + 2) + 64) * sizeof(uint32_t));
+    L->incb = take(ntiles * 64 + 64);
     L->tile_bytes = take((ntiles + 1) * sizeof(uint32_t));
     L->tile_local = take((ntiles + 1) * sizeof(uint32_t));
     L->group_total = take((ngroups + 1) * sizeof(uint64_t));
@@ -762,7 +927,7 @@ cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
     cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(
         reinterpret_cast<const uint32_t*>(d_in), nquads, ntiles, nruns, reinterpret_cast<uint32_t*>(ws + L.sigw),
         reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
-        reinterpret_cast<uint32_t*>(ws + L.final_tab));
+        reinterpret_cast<uint32_t*>(ws + L.final_tab), nullptr, nullptr);
     ++*launches;
     if (ev) cudaEventRecord(ev[1], stream);
     if (d_table_out) {
@@ -799,8 +964,34 @@ cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
                                                    reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
     ++*launches;
     if (allow_protected_fallback) {
-        // Runs only when the quiet check failed: recompute signatures + copy map exactly, then the sizes again.
-        cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, st, 1, sigw, copymap);
+        // Everything below exits immediately unless the quiet check failed (status->nonquiet).
+        // 1) parallel fixed-point iteration of the copy map; 2) if it does not converge in PROT_ITERS rounds, the exact
+        //    in-order walk; 3) the sizes again, now with the copy map.
+        uint8_t* copymap2 = ws + L.copymap2;
+        uint32_t* seg_state = reinterpret_cast<uint32_t*>(ws + L.seg_state);
+        uint8_t* incb = ws + L.incb;
+        int num_ctas = 0;
+        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_ctas, cudaDevAttrMultiProcessorCount, dev); if (num_ctas < 1) num_ctas = 1; }
+        const uint32_t nseg = (uint32_t)((nblocks + PSEG - 1) / PSEG);
+        const uint32_t* in32 = reinterpret_cast<const uint32_t*>(d_in);
+        const uint64_t nquads = nbytes / 4;
+        constexpr int PROT_ITERS = 4;
+        for (int it = 0; it <= PROT_ITERS; ++it) {
+            if (it > 0) {   // flags under the current copy map (copy-mode blocks hidden from the dictionary)
+                cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(in32, nquads, ntiles, nruns, sigw,
+                    reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+                    reinterpret_cast<uint32_t*>(ws + L.final_tab), copymap, st);
+                cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
+                                                                reinterpret_cast<uint32_t*>(ws + L.carry), nullptr, st);
+                cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+                                                                 reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw, st);
+                *launches += 3;
+            }
+            prot_iterate<<<num_ctas, PI_THREADS, 0, stream>>>(sigw, nbytes, nblocks, nseg, st, it, incb, copymap, copymap2,
+                                                              seg_state, seg_state + (nseg + 1));
+            ++*launches;
+        }
+        cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(in32, nbytes, st, 1, sigw, copymap);
         ++*launches;
         cham_tile_sizes<<<ts_blocks, 256, 0, stream>>>(sigw, copymap, nbytes, nblocks, ntiles, 1, 0, 0, st,
                                                        reinterpret_cast<uint32_t*>(ws + L.tile_bytes));

@@ -75,7 +75,11 @@ struct Status {
     unsigned int nonquiet;          // fast path invalid: protection automaton would have fired
     unsigned int error;             // 0 ok; see density_b200.h DENSITY_B200_E*
     unsigned long long first_nonquiet_block;
-    unsigned int pad[2];
+    unsigned int converged;         // copy map reached its fixed point (parallel protection iteration)
+    unsigned int iter_changed;      // scratch of the iteration's compare step
+    unsigned int barrier[8];        // grid barriers of the protection iteration kernels (one per launch)
+    unsigned int relax_changed[2];  // ping-pong "some segment was re-evaluated in this round"
+    unsigned int pad2[2];
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }

@@ -8,7 +8,7 @@ namespace dns {
 
 // byte offsets of the Chameleon encode scratch arrays inside one workspace allocation
 struct ChamLayout {
-    size_t status, sigw, copymap, tile_bytes, tile_local, group_total, group_off, unres, unres_count, final_tab, carry, total;
+    size_t status, sigw, copymap, copymap2, seg_state, incb, tile_bytes, tile_local, group_total, group_off, unres, unres_count, final_tab, carry, total;
 };
 
 size_t cham_workspace_bytes(size_t nbytes, int nruns_max, ChamLayout* L);

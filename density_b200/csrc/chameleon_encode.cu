@@ -771,6 +771,16 @@ cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, co
     const bool use_cm = copymap && (!use_copymap_if_nonquiet || status->nonquiet);
     const uint64_t tile_off = group_off[tile / SCAN_G] + tile_local[tile];
     const uint64_t nquads = nbytes / 4;
+    // Issue all 16 input loads of this thread first (4 block pairs x 4 sub-rows): the kernel is latency-bound on them otherwise.
+    uint32_t qv[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t gq = ((uint64_t)tile * 64 + (warp + 8 * i) * 2 + (j >> 1)) * 64 + (j & 1) * 32 + lane;
+            qv[i * 4 + j] = (gq < nquads) ? ld_stream_u32(in + gq) : 0u;
+        }
+    }
 
     if (tid < 64) {
         const uint64_t b = (uint64_t)tile * 64 + tid;
@@ -793,9 +803,12 @@ cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, co
     __syncthreads();
 
     const uint8_t* in_b = reinterpret_cast<const uint8_t*>(in);
-    for (uint32_t bp = warp; bp < 32; bp += EM_THREADS / 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t bp = warp + 8 * i;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            const uint32_t q = qv[i * 4 + j];
             const uint32_t bl = bp * 2 + (j >> 1);                   // block within tile
             const uint64_t b = (uint64_t)tile * 64 + bl;
             if (b >= nblocks) continue;                               // warp-uniform
@@ -807,7 +820,6 @@ cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, co
                 const uint64_t boff = b * 256;
                 const uint32_t blen = (uint32_t)((nbytes - boff < 256) ? (nbytes - boff) : 256);
                 if (gq < nquads && k * 4 + 4 <= blen) {
-                    uint32_t q = in[gq];
                     st_u16(bout + 4 * k, q & 0xFFFFu); st_u16(bout + 4 * k + 2, q >> 16);
                 }
                 if ((j & 1) == 1 && lane < (blen & 3u)) bout[(blen & ~3u) + lane] = in_b[boff + (blen & ~3u) + lane];
@@ -819,7 +831,6 @@ cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, co
                 st_u16(bout + 2 * lane, ((lane < 2 ? lo : hi) >> (16 * (lane & 1))) & 0xFFFFu);
             }
             if (gq < nquads) {
-                const uint32_t q = in[gq];
                 const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
                 const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
                 uint8_t* p = bout + 8 + 4 * k - 2 * before;

@@ -28,6 +28,7 @@
 // If two consecutive blocks are incompressible the automaton may switch to copy mode, which removes blocks
 // from the dictionary history. That case is handled by cham_protected_pass: an exact, in-order,
 // protection-aware single-CTA walk (also the device-side checker for the fast path in the tests).
+#include <cstdio>
 #include "common.cuh"
 #include "encode_internal.cuh"
 
@@ -50,7 +51,7 @@ constexpr int CLS_CAP = 128;                       // entries per class list; ov
 // Compacted per-tile record of a misser (or of a hit member that turned out to need the slow path):
 //   x = hash | fp << 16
 //   y = pos(12) | touched << 12 | slow << 13 | first << 14 | setter << 15 | old_fp << 16
-constexpr uint32_t R_TOUCHED = 1u << 12, R_SLOW = 1u << 13, R_FIRST = 1u << 14, R_SETTER = 1u << 15;
+constexpr uint32_t R_TOUCHED = 1u << 12, R_SLOW = 1u << 13, R_FIRST = 1u << 14;
 
 struct FlagSmem {
     uint16_t tab[65536];          // fingerprint of the last quad seen in each bucket
@@ -138,8 +139,11 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4* t4 = reinterpret_cast<uint4*>(S.tab);
+        #pragma unroll 1
         for (uint32_t i = tid; i < 65536 * 2 / 16; i += FP_THREADS) t4[i] = z;
+        #pragma unroll 1
         for (uint32_t i = tid; i < 2048; i += FP_THREADS) { S.vbit[i] = 0; S.conf[i] = 0; }
+        #pragma unroll 1
         for (uint32_t i = tid; i < SIDE_N; i += FP_THREADS) S.side[i] = SIDE_EMPTY;
         if (tid < CLS_N) S.cls_count[tid] = 0;
         if (tid == 0) { S.unres_count = 0; S.cls_overflow = 0; S.nrec = 0; }
@@ -155,6 +159,13 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < rem) ? ld_stream_u32(in + q0 + pos0 + 32 * j) : 0u;
     }
 
+#ifdef DNS_PHASE_TIMING
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define DNS_PH(k) { long long tn = clock64(); ph[k] += tn - tprev; tprev = tn; }
+#else
+#define DNS_PH(k)
+#endif
+    #pragma unroll 1
     for (uint64_t t = t_begin; t < t_end; ++t) {
         uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT];
         const uint64_t tile_q0 = t * TILE_Q;
@@ -180,7 +191,6 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         }
         // ---- phase A: read the pre-tile dictionary; compact the missers into S.rec --------------------
         uint32_t missmask = 0;    // bit j: my sub-row j quad missed
-        uint32_t setmask = 0;     // bit j: I raised the conflict bit of that quad's bucket (hit member gone slow)
         {
             uint32_t old[FP_QPT], tch = 0;
 #pragma unroll
@@ -215,9 +225,11 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             }
         }
         __syncthreads();  // S1: all reads of tab/vbit precede the publishes; S.nrec = number of missers
+        DNS_PH(0)
         const uint32_t nmiss = S.nrec;  // stable until phase C appends behind it
 
         // ---- phase B: missers publish ---------------------------------------------------------------
+        #pragma unroll 1
         for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
             const uint2 r = S.rec[i];
             const uint32_t hh = r.x & 0xFFFFu;
@@ -225,6 +237,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             atomicMin(&S.side[hh & (SIDE_N - 1)], ((r.y & 0xFFFu) << 16) | hh);
         }
         __syncthreads();  // S2
+        DNS_PH(1)
 
         // ---- phase C: read back ----------------------------------------------------------------------
         // hit members: the bucket still holds my value unless some misser published (its value differs from mine)
@@ -246,7 +259,6 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
                         const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
                         if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)idx; else S.cls_overflow = 1;
                         atomicOr(&S.conf[h[j] >> 5], 1u << (h[j] & 31));
-                        setmask |= 1u << j;
                     }
                 }
             }
@@ -254,6 +266,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             if (lane == 0) S.sigw[warp * 4 + j] = fb;
         }
         // missers: do all missers of my bucket agree, and who is first?
+        #pragma unroll 1
         for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
             const uint2 r = S.rec[i];
             const uint32_t hh = r.x & 0xFFFFu;
@@ -261,7 +274,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             const uint32_t w = S.tab[hh];
             uint32_t y = r.y;
             if ((slot & 0xFFFFu) != hh || w != (r.x >> 16)) {   // foreign slot owner, or missers disagree
-                y |= R_SLOW | R_SETTER;
+                y |= R_SLOW;
                 atomicOr(&S.conf[hh >> 5], 1u << (hh & 31));
             } else if (slot == (((r.y & 0xFFFu) << 16) | hh)) {
                 y |= R_FIRST;
@@ -269,8 +282,10 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             if (y != r.y) S.rec[i].y = y;
         }
         __syncthreads();  // S3
+        DNS_PH(2)
 
         // ---- phase D: missers classify ----------------------------------------------------------------
+        #pragma unroll 1
         for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
             const uint2 r = S.rec[i];
             const uint32_t hh = r.x & 0xFFFFu;
@@ -287,18 +302,17 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
         }
         __syncthreads();  // S4
+        DNS_PH(3)
 
         // ---- phase F ------------------------------------------------------------------------------------
+        S.conf[tid] = 0; S.conf[tid + FP_THREADS] = 0;   // all readers of the conflict bits are behind S4; next set in the next tile's phase C
         if (S.cls_overflow) {
             // restore the pre-tile dictionary (only missers wrote), clear the per-tile state, walk the tile in order
+            #pragma unroll 1
             for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
                 const uint2 r = S.rec[i];
                 S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
-                if (r.y & R_SETTER) atomicAnd(&S.conf[(r.x & 0xFFFFu) >> 5], ~(1u << (r.x & 31)));
             }
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j)
-                if (setmask & (1u << j)) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
             if (tid < CLS_N) S.cls_count[tid] = 0;
             __syncthreads();
             uint32_t* qs = reinterpret_cast<uint32_t*>(S.rec);
@@ -309,6 +323,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run, copymap ? copymap + t * 64 : nullptr);
         } else {
             // first missers of agreeing buckets: genuine miss or unresolved first touch; deferred vbit; conflict-bit cleanup
+            #pragma unroll 1
             for (uint32_t base = warp * 32; base < nmiss; base += FP_THREADS) {
                 const uint32_t i = base + lane;
                 uint2 r = make_uint2(0, 0);
@@ -316,16 +331,13 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
                 const uint32_t hh = r.x & 0xFFFFu;
                 const bool first = (i < nmiss) && (r.y & (R_FIRST | R_SLOW)) == R_FIRST;
                 if (first && (r.x >> 16) == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-                if (r.y & R_SETTER) atomicAnd(&S.conf[hh >> 5], ~(1u << (hh & 31)));
                 append_unres(first && !(r.y & R_TOUCHED), run_q0 + (r.y & 0xFFFu), hh, r.x >> 16, &S.unres_count, unres_run);
             }
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j)
-                if (setmask & (1u << j)) atomicAnd(&S.conf[h[j] >> 5], ~(1u << (h[j] & 31)));
             // slow members, warp w <- class w. In-order semantics per bucket: my predecessor is the member of my bucket
             // with the largest smaller position; without one the pre-tile value decides. The last member's value stays.
             const uint32_t n = S.cls_count[warp];
             const uint16_t* __restrict__ lst = S.cls_list[warp];
+            #pragma unroll 1
             for (uint32_t base = 0; base < n; base += 32) {
                 const uint32_t i = base + lane;
                 const bool valid = i < n;
@@ -335,6 +347,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
                     hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & 0xFFFu; touched = (d.y & R_TOUCHED) != 0; oldv = d.y >> 16;
                 }
                 int best = -1; uint32_t bestf = 0; bool later = false;
+                #pragma unroll 1
                 for (uint32_t k = 0; k < n; ++k) {
                     const uint2 dk = S.rec[lst[k]];      // broadcast reads
                     const uint32_t pk = dk.y & 0xFFFu;
@@ -356,12 +369,19 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             if (tid == 0) S.nrec = 0;
         }
         __syncthreads();  // S5: dictionary final for this tile, sigw final
+        DNS_PH(4)
 
         if (tid < TILE_Q / 32) sigw_g[tile_q0 / 32 + tid] = S.sigw[tid];  // workspace is sized in whole tiles
         // (the next iteration rewrites S.sigw only after two more barriers)
     }
 
+#ifdef DNS_PHASE_TIMING
+    if (tid == 0 && run == 77) { const long long nt = (long long)(t_end - t_begin);
+        printf("run %u tiles %lld cycles/tile: A %lld B %lld C %lld D %lld F %lld  total %lld\n", run, nt,
+               ph[0] / nt, ph[1] / nt, ph[2] / nt, ph[3] / nt, ph[4] / nt, (ph[0] + ph[1] + ph[2] + ph[3] + ph[4]) / nt); }
+#endif
     // ---- export the run's last-writer table ---------------------------------------------------------
+    #pragma unroll 1
     for (uint32_t i = tid; i < 65536; i += FP_THREADS) {
         uint32_t v = S.tab[i];
         uint32_t tch = (v != 0 || bit_test(S.vbit, i)) ? 0x10000u : 0u;

@@ -134,6 +134,14 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
     const uint64_t t_end = (uint64_t)(run + 1) * tiles_total / nruns;
     uint2* __restrict__ unres_run = unres + (size_t)run * 65536;
     const uint32_t pos0 = warp * 128 + lane;  // position of my sub-row 0 quad inside a tile; sub-row j adds 32*j
+    // run-relative 32-bit geometry (a run is < 2^32 quads): keeps 64-bit compares out of the tile loop
+    const uint32_t ntile_run = (uint32_t)(t_end - t_begin);
+    const uint64_t q_begin = t_begin * TILE_Q;
+    const uint64_t q_end64 = (t_end * TILE_Q < nquads) ? t_end * TILE_Q : nquads;
+    const uint32_t run_quads = q_begin < q_end64 ? (uint32_t)(q_end64 - q_begin) : 0u;
+    const uint32_t* __restrict__ rin = in + q_begin;
+    uint32_t* __restrict__ rsig = sigw_g + t_begin * (TILE_Q / 32);
+    const uint8_t* __restrict__ rcm = copymap ? copymap + t_begin * 64 : nullptr;
 
     // ---- init shared state -------------------------------------------------------------------------
     {
@@ -152,12 +160,8 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 
     // ---- prefetch the first tile --------------------------------------------------------------------
     uint32_t nxt[FP_QPT];
-    {
-        const uint64_t q0 = t_begin * TILE_Q;
-        const uint32_t rem = (t_begin < t_end && q0 < nquads) ? (uint32_t)((nquads - q0 < TILE_Q) ? (nquads - q0) : TILE_Q) : 0u;
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < rem) ? ld_stream_u32(in + q0 + pos0 + 32 * j) : 0u;
-    }
+    for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < run_quads) ? ld_stream_u32(rin + pos0 + 32 * j) : 0u;
 
 #ifdef DNS_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -166,25 +170,24 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 #define DNS_PH(k)
 #endif
     #pragma unroll 1
-    for (uint64_t t = t_begin; t < t_end; ++t) {
+    for (uint32_t lt = 0; lt < ntile_run; ++lt) {
         uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT];
-        const uint64_t tile_q0 = t * TILE_Q;
-        const uint32_t rem = (tile_q0 < nquads) ? (uint32_t)((nquads - tile_q0 < TILE_Q) ? (nquads - tile_q0) : TILE_Q) : 0u;
-        const uint32_t run_q0 = (uint32_t)((t - t_begin) * TILE_Q);
+        const uint32_t run_q0 = lt * TILE_Q;                                  // first quad of the tile, relative to the run
+        const uint32_t left = run_q0 < run_quads ? run_quads - run_q0 : 0u;   // quads left in the run from here
+        const uint32_t rem = left < (uint32_t)TILE_Q ? left : (uint32_t)TILE_Q;
 #pragma unroll
         for (int j = 0; j < FP_QPT; ++j) q[j] = nxt[j];
         {   // prefetch next tile (register double buffer; consumed one full tile later)
-            const uint64_t q0 = tile_q0 + TILE_Q;
-            const uint32_t nrem = (t + 1 < t_end && q0 < nquads) ? (uint32_t)((nquads - q0 < TILE_Q) ? (nquads - q0) : TILE_Q) : 0u;
-            const uint32_t* __restrict__ np = in + q0 + pos0;
+            const uint32_t nleft = left > (uint32_t)TILE_Q ? left - TILE_Q : 0u;
+            const uint32_t* __restrict__ np = rin + run_q0 + TILE_Q + pos0;
 #pragma unroll
-            for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nrem) ? ld_stream_u32(np + 32 * j) : 0u;
+            for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nleft) ? ld_stream_u32(np + 32 * j) : 0u;
         }
 
         uint32_t actmask = 0;     // bit j: my sub-row j quad exists and its block is not in copy mode
         {
             uint32_t cp = 0;      // bit 0/1: block 2*warp / 2*warp+1 of this tile is a copy-mode block
-            if (copymap) cp = (copymap[t * 64 + warp * 2] ? 1u : 0u) | (copymap[t * 64 + warp * 2 + 1] ? 2u : 0u);
+            if (rcm) cp = (rcm[lt * 64 + warp * 2] ? 1u : 0u) | (rcm[lt * 64 + warp * 2 + 1] ? 2u : 0u);
 #pragma unroll
             for (int j = 0; j < FP_QPT; ++j)
                 if (pos0 + 32 * j < rem && !((cp >> (j >> 1)) & 1u)) actmask |= 1u << j;
@@ -320,7 +323,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
             for (int j = 0; j < FP_QPT; ++j) qs[pos0 + 32 * j] = q[j];
             if (tid == 0) { S.nrec = 0; S.cls_overflow = 0; }
             __syncthreads();
-            if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run, copymap ? copymap + t * 64 : nullptr);
+            if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run, rcm ? rcm + lt * 64 : nullptr);
         } else {
             // first missers of agreeing buckets: genuine miss or unresolved first touch; deferred vbit; conflict-bit cleanup
             #pragma unroll 1
@@ -371,12 +374,12 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         __syncthreads();  // S5: dictionary final for this tile, sigw final
         DNS_PH(4)
 
-        if (tid < TILE_Q / 32) sigw_g[tile_q0 / 32 + tid] = S.sigw[tid];  // workspace is sized in whole tiles
+        if (tid < TILE_Q / 32) rsig[lt * (TILE_Q / 32) + tid] = S.sigw[tid];  // workspace is sized in whole tiles
         // (the next iteration rewrites S.sigw only after two more barriers)
     }
 
 #ifdef DNS_PHASE_TIMING
-    if (tid == 0 && run == 77) { const long long nt = (long long)(t_end - t_begin);
+    if (tid == 0 && run == 77) { const long long nt = (long long)ntile_run;
         printf("run %u tiles %lld cycles/tile: A %lld B %lld C %lld D %lld F %lld  total %lld\n", run, nt,
                ph[0] / nt, ph[1] / nt, ph[2] / nt, ph[3] / nt, ph[4] / nt, (ph[0] + ph[1] + ph[2] + ph[3] + ph[4]) / nt); }
 #endif

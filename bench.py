@@ -323,8 +323,14 @@ def run_ours(args):
         }
         dom = "cham_flag_pass" if fp >= em else "cham_emit"
         ach = kernels[dom]["gbs"]
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+        try:
+            if n == GiB:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"][dom]
+        except Exception:
+            traffic = None
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                            "frac": (ach / peak_gbs) if ach else None, "traffic": None, "peak_source": peak_src,
+                            "frac": (ach / peak_gbs) if ach else None, "traffic": traffic, "peak_source": peak_src,
                             "step_algorithmic": {"bytes": n + out_bytes, "achieved": step_alg, "frac": step_alg / peak_gbs},
                             "input_rate_frac": value / peak_gbs, "kernels": kernels}
     if extra:

@@ -135,6 +135,16 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
             if (ev != nullptr && e == cudaSuccess) c->prof_count++;
         }
         c->last_was_chameleon_fastpath_capable = (path != 2);
+    } else if (alg == ALG_CHEETAH && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 3) && !(reinterpret_cast<uintptr_t>(d_out) & 1)) {
+        // run-parallel Cheetah encoder; the exact in-order kernel is queued behind it and only runs if the copy map did not settle
+        const size_t pw = (chee_workspace_bytes(n, c->num_sms) + 255) & ~(size_t)255;
+        e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg));
+        if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+        uint32_t* d_conv = reinterpret_cast<uint32_t*>(c->ws.p + pw);
+        e = chee_encode_parallel(d_in, n, d_out, cap, c->ws.p, c->num_sms, d_out_size, d_conv, stream, &launches);
+        if (e == cudaSuccess && path != 1)
+            e = scalar_encode(alg, d_in, n, d_out, cap, c->ws.p + pw + 256, d_out_size, stream, &launches, d_conv);
+        c->last_was_chameleon_fastpath_capable = 0;
     } else {
         if (reinterpret_cast<uintptr_t>(d_out) & 1) { set_error("encode_device: d_out must be 2-byte aligned"); return DENSITY_B200_EARG; }
         e = c->ws.ensure(scalar_workspace_bytes(alg));

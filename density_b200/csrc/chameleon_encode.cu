@@ -570,8 +570,9 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
     unsigned int* bar = &st->barrier[it & 7];
 
     // (1) incompressible bits of the blocks that were encoded in the pass just finished
-    for (uint64_t b = gtid; b < nblocks; b += gsz)
-        if (!(it && cm_old[b])) inc[b] = (nbytes - b * 256 >= 256) && (__popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]) <= 4);
+    if (sigw_g)   // Chameleon: derive the bits from the signatures; other codecs pass sigw_g == nullptr and fill `inc` themselves
+        for (uint64_t b = gtid; b < nblocks; b += gsz)
+            if (!(it && cm_old[b])) inc[b] = (nbytes - b * 256 >= 256) && (__popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]) <= 4);
     if (gtid == 0) { st->relax_changed[0] = 0; st->relax_changed[1] = 0; st->iter_changed = 0; }
     grid_barrier(bar, gridDim.x, epoch);
 
@@ -1051,6 +1052,18 @@ cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
 cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches) {
     cham_status_accumulate_k<<<1, 1, 0, stream>>>(reinterpret_cast<const Status*>(ws + L.status), d_flag);
     ++*launches;
+    return cudaGetLastError();
+}
+cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* st, int it, uint8_t* inc,
+                                uint8_t* cm_old, uint8_t* cm_new, uint32_t* in_state, uint32_t* out_state, int /*block_bytes*/, int num_sms,
+                                cudaStream_t stream) {
+    prot_iterate<<<num_sms > 0 ? num_sms : 1, PI_THREADS, 0, stream>>>(sigw_or_null, nbytes, nblocks, nseg, st, it, inc, cm_old, cm_new, in_state, out_state);
+    return cudaGetLastError();
+}
+cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint32_t* tile_local, uint64_t* group_total, uint64_t* group_off,
+                              uint32_t ngroups, Status* st, uint64_t cap, uint64_t* d_out_size, cudaStream_t stream) {
+    scan_groups_local<<<ngroups, SCAN_T, 0, stream>>>(tile_bytes, ntiles, tile_local, group_total);
+    scan_group_totals<<<1, SCAN_T, 0, stream>>>(group_total, ngroups, group_off, st, cap, d_out_size);
     return cudaGetLastError();
 }
 cudaError_t cham_table_init(uint32_t* d_table, cudaStream_t stream, uint64_t* launches) {

@@ -22,6 +22,19 @@ cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
 cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out,
                                        size_t cap, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
 
+// shared pieces of the encoders (chameleon_encode.cu)
+struct Status;
+cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* st, int it, uint8_t* inc,
+                                uint8_t* cm_old, uint8_t* cm_new, uint32_t* in_state, uint32_t* out_state, int block_bytes, int num_sms,
+                                cudaStream_t stream);
+cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint32_t* tile_local, uint64_t* group_total, uint64_t* group_off,
+                              uint32_t ngroups, Status* st, uint64_t cap, uint64_t* d_out_size, cudaStream_t stream);
+
+// cheetah_encode.cu
+size_t chee_workspace_bytes(size_t nbytes, int num_sms);
+cudaError_t chee_encode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, int num_sms,
+                                 uint64_t* d_out_size, uint32_t* d_converged, cudaStream_t stream, uint64_t* launches);
+
 // chameleon_decode.cu
 size_t cham_decode_workspace_bytes(size_t nbytes, int nruns_max);
 cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, int num_sms,
@@ -30,7 +43,7 @@ cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
 // scalar_codec.cu (Cheetah / Lion, in-order)
 size_t scalar_workspace_bytes(int alg);
 cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if_zero = nullptr);
 cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
                           uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if = nullptr);
 

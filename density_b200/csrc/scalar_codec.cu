@@ -78,8 +78,9 @@ struct Enc {
 
 template <int ALG>
 __global__ void encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, Tables T,
-                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size) {
+                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if_zero) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (run_if_zero && *run_if_zero != 0) return;   // the parallel encoder already produced the result
     constexpr uint32_t B = ALG == ALG_CHAMELEON ? 256 : ALG == ALG_CHEETAH ? 128 : 64;
     constexpr uint32_t SB = ALG == ALG_LION ? 6 : 8;
     Enc<ALG> E; E.T = T; E.out = out; E.cap = cap;
@@ -250,15 +251,15 @@ static scalar::Tables carve(int alg, uint8_t* ws) {
 }
 
 cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches) {
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if_zero) {
     cudaError_t e = cudaMemsetAsync(ws, 0, scalar_workspace_bytes(alg), stream);  // X::new(): zeroed tables
     if (e != cudaSuccess) return e;
     scalar::Tables T = carve(alg, ws);
     Status* st = reinterpret_cast<Status*>(ws);
     switch (alg) {
-    case ALG_CHAMELEON: scalar::encode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size); break;
-    case ALG_CHEETAH:   scalar::encode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size); break;
-    default:            scalar::encode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size); break;
+    case ALG_CHAMELEON: scalar::encode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero); break;
+    case ALG_CHEETAH:   scalar::encode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero); break;
+    default:            scalar::encode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero); break;
     }
     ++*launches;
     return cudaGetLastError();

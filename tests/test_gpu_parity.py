@@ -319,3 +319,24 @@ def test_chameleon_decode_adversarial_same_bucket(torch_cuda, codecs):
     assert copied == 0
     dec = gpu_decode(codecs["chameleon"], enc, data.size)
     assert dec.size == data.size and (dec == data).all()
+
+
+@pytest.mark.parametrize("path", [0, 1, 3])
+@pytest.mark.parametrize("kind,nbytes", [("text", 300), ("text", 4096 + 3), ("text", 70001), ("text", (1 << 20) + 5), ("text", 6 * (1 << 20) + 2),
+                                         ("mixed", 3 * (1 << 20) + 1), ("random", 1 << 20), ("zeros", 1 << 20), ("low", 500000)])
+def test_cheetah_encode_paths(torch_cuda, codecs, path, kind, nbytes):
+    """path 0 auto (run-parallel encoder, in-order kernel if the copy map does not settle), 1 run-parallel only, 3 in-order kernel."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    if path == 3 and nbytes > (1 << 20) + 5:
+        pytest.skip("in-order kernel is slow")
+    data = synth.synth_text(nbytes).numpy() if kind == "text" else (synth.synth_mixed(nbytes).numpy() if kind == "mixed" else payload(kind, nbytes, 7))
+    want = oracle.encode("cheetah", data)
+    d_in = torch.from_numpy(data.copy()).cuda()
+    d_out = torch.zeros(codecs["cheetah"].safe_encode_buffer_size(nbytes) + 64, dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("cheetah", d_in, d_out, d_sz, path=path)
+    torch.cuda.synchronize()
+    n = int(d_sz.item())
+    assert n == want.size and (d_out[:n].cpu().numpy() == want).all()

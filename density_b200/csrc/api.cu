@@ -38,7 +38,7 @@ struct DevBuf {
         size_t want = need + need / 8 + 4096;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { e = cudaMalloc(&p, need); want = need; }
-        if (e == cudaSuccess) bytes = want;
+        if (e == cudaSuccess) { bytes = want; e = cudaMemset(p, 0, want); }   // the Cheetah run tables rely on starting out zeroed
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
@@ -51,6 +51,8 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;     // for the synchronous host-pointer entry points (compute)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the pipelined host path
     DevBuf ws, stage_in, stage_out, pipe_tables;
+    DevBuf chee_tables;                // epoch-tagged run tables of the Cheetah encoder (zero at allocation, never shared)
+    uint32_t chee_epoch = 0;
     uint64_t* h_sizes = nullptr;       // pinned, PIPE_MAX_CHUNKS entries
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     uint64_t* d_size = nullptr;        // 8 B device
@@ -140,8 +142,17 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
         const size_t pw = (chee_workspace_bytes(n, c->num_sms) + 255) & ~(size_t)255;
         e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg));
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+        if (e == cudaSuccess) e = c->chee_tables.ensure(chee_tables_bytes(n, c->num_sms));
+        if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+        if (c->chee_epoch > 0x3FFFFF00u) {                 // epochs exhausted (2^26 calls): start over on cleared tables
+            e = cudaMemsetAsync(c->chee_tables.p, 0, c->chee_tables.bytes, stream);
+            if (e != cudaSuccess) { set_error("cudaMemsetAsync", e); return DENSITY_B200_ECUDA; }
+            c->chee_epoch = 0;
+        }
+        const uint32_t epoch_base = c->chee_epoch + 1;
+        c->chee_epoch += 16;
         uint32_t* d_conv = reinterpret_cast<uint32_t*>(c->ws.p + pw);
-        e = chee_encode_parallel(d_in, n, d_out, cap, c->ws.p, c->num_sms, d_out_size, d_conv, stream, &launches);
+        e = chee_encode_parallel(d_in, n, d_out, cap, c->ws.p, c->chee_tables.p, epoch_base, c->num_sms, d_out_size, d_conv, stream, &launches);
         if (e == cudaSuccess && path != 1)
             e = scalar_encode(alg, d_in, n, d_out, cap, c->ws.p + pw + 256, d_out_size, stream, &launches, d_conv);
         c->last_was_chameleon_fastpath_capable = 0;
@@ -488,7 +499,7 @@ void density_b200_shutdown(void) {
         DeviceCtx& c = g_ctx[d];
         if (!c.ready) continue;
         cudaSetDevice(d);
-        c.ws.release(); c.stage_in.release(); c.stage_out.release();
+        c.ws.release(); c.stage_in.release(); c.stage_out.release(); c.chee_tables.release(); c.chee_epoch = 0;
         if (c.d_size) cudaFree(c.d_size);
         if (c.h_size) cudaFreeHost(c.h_size);
         if (c.stream) cudaStreamDestroy(c.stream);

@@ -30,15 +30,6 @@ namespace chee {
 constexpr int TILE_B = 128;                 // blocks per tile (4096 quads = 16 KiB), the unit of run geometry and of the emit grid
 constexpr uint32_t FP_INVALID = 0x10000u;   // a fingerprint value that matches nothing (bucket h != 0 initially "holds quad 0")
 
-struct RunTables {            // per run, in global memory
-    uint32_t* tabP;           // [65536] last quad seen in each context
-    uint32_t* u1P;            // [65536] 1 + quad index of the run's first (unresolved) access of the context; 0 = untouched
-    uint32_t* tabC;           // [65536] a | b << 16
-    uint32_t* u1C;            // [65536] 1 + quad index of the first access of the bucket (valid if stC != 0)
-    uint32_t* u2C;            // [65536] 1 + quad index of the first access that differs from it (valid if stC == 2)
-    uint8_t* stC;             // [65536] 0 untouched, 1 a known, 2 a and b known
-};
-
 __device__ __forceinline__ uint64_t run_block_begin(uint32_t r, uint32_t nruns, uint64_t ntiles) { return ((uint64_t)r * ntiles / nruns) * TILE_B; }
 
 // context of the first encoded quad of every run: hash of the last quad of the last encoded block before the run (0 if none)
@@ -62,44 +53,50 @@ __global__ void chee_ctx0(const uint32_t* __restrict__ in, uint64_t nquads, cons
 constexpr int RP_WARPS = 4;   // warps (runs) per CTA
 
 // ---- pass P: PREDICTED flags ----------------------------------------------------------------------------------------------
+// Table entry per (run, context): {last quad seen, epoch, 1 + index of the run's first (unresolved) access, 0}. An entry whose epoch
+// differs from the current round's is "untouched": no memset between rounds / calls (the workspace is zeroed once, epochs start at 1).
 __global__ void __launch_bounds__(RP_WARPS * 32)
 chee_pass_p(const uint32_t* __restrict__ in, uint64_t nquads, uint64_t nblocks, const uint8_t* __restrict__ copymap, uint32_t nruns, uint64_t ntiles,
-            const Status* __restrict__ gate, const uint32_t* __restrict__ ctx0, uint32_t* __restrict__ tabP_all, uint32_t* __restrict__ u1P_all,
+            const Status* __restrict__ gate, const uint32_t* __restrict__ ctx0, uint4* __restrict__ entP_all, uint32_t epoch,
             uint32_t* __restrict__ Pbits) {
     if (gate && !(gate->nonquiet && !gate->converged)) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (r >= nruns) return;
-    uint32_t* __restrict__ tabP = tabP_all + (size_t)r * 65536;
-    uint32_t* __restrict__ u1P = u1P_all + (size_t)r * 65536;
+    uint4* __restrict__ entP = entP_all + (size_t)r * 65536;
     const uint64_t b0 = run_block_begin(r, nruns, ntiles);
     uint64_t b1 = run_block_begin(r + 1, nruns, ntiles);
     if (b1 > nblocks) b1 = nblocks;
     uint32_t last_h = ctx0[r];
+    uint32_t qn = (b0 < b1 && b0 * 32 + lane < nquads) ? ld_stream_u32(in + b0 * 32 + lane) : 0u;   // software prefetch, one block ahead
     for (uint64_t b = b0; b < b1; ++b) {
+        const uint32_t q = qn;
+        if (b + 1 < b1) qn = ((b + 1) * 32 + lane < nquads) ? ld_stream_u32(in + (b + 1) * 32 + lane) : 0u;
         if (copymap && copymap[b]) { if (lane == 0) Pbits[b] = 0; continue; }
         const uint64_t q0 = b * 32;
         const uint32_t nq = (q0 >= nquads) ? 0u : (uint32_t)((nquads - q0 < 32) ? (nquads - q0) : 32);
         if (nq == 0) { if (lane == 0) Pbits[b] = 0; continue; }
         const bool active = lane < nq;
-        const uint32_t q = active ? ld_stream_u32(in + q0 + lane) : 0u;
         const uint32_t h = prod_hash(hash_prod(q));
         const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h, 1);
         const uint32_t ctx = lane ? hp : last_h;
         last_h = __shfl_sync(0xFFFFFFFFu, h, nq - 1);
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (active) e = __ldcg(&entP[ctx]);                           // issued for every lane up front: one 16-byte access
         const uint32_t key = active ? ctx : 0x10000u + lane;
         const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
         const uint32_t lower = grp & lanemask_lt();
         const int src = lower ? 31 - __clz(lower) : 0;
         const uint32_t qprev = __shfl_sync(0xFFFFFFFFu, q, src);
-        bool known = lower != 0; uint32_t pv = qprev;
-        if (active && !lower) {
-            known = __ldcg(&u1P[ctx]) != 0;
-            pv = known ? __ldcg(&tabP[ctx]) : 0u;
-            if (!known) u1P[ctx] = (uint32_t)(q0 + lane) + 1u;       // unresolved first access of this context in the run
-        }
+        const bool touched = e.y == epoch;
+        const bool known = lower != 0 || touched;
+        const uint32_t pv = lower ? qprev : e.x;
         const bool P = active && known && pv == q;
-        if (active && (grp & lanemask_gt()) == 0) tabP[ctx] = q;     // cheetah.rs:144 (and :148 is implied: predicted == already equal)
+        // the group's first lane owns the "first access" slot, its last lane leaves the value (cheetah.rs:144; :148 is implied)
+        uint32_t u1 = touched ? e.z : 0u;
+        if (active && !lower && !touched) u1 = (uint32_t)(q0 + lane) + 1u;
+        const uint32_t u1g = __shfl_sync(0xFFFFFFFFu, u1, __ffs(grp) - 1);
+        if (active && (grp & lanemask_gt()) == 0) entP[ctx] = make_uint4(q, epoch, u1g, 0u);
         const uint32_t pm = __ballot_sync(0xFFFFFFFFu, P);
         if (lane == 0) Pbits[b] = pm;
         __syncwarp();
@@ -107,80 +104,86 @@ chee_pass_p(const uint32_t* __restrict__ in, uint64_t nquads, uint64_t nblocks, 
 }
 
 // walk the runs in order per context: resolve each run's first access from the carried-in value, carry the run's last value on
-__global__ void chee_fold_p(const uint32_t* __restrict__ in, uint32_t nruns, const Status* __restrict__ gate, const uint32_t* __restrict__ tabP_all,
-                            const uint32_t* __restrict__ u1P_all, uint32_t* __restrict__ Pbits) {
+__global__ void chee_fold_p(const uint32_t* __restrict__ in, uint32_t nruns, const Status* __restrict__ gate, const uint4* __restrict__ entP_all,
+                            uint32_t epoch, uint32_t* __restrict__ Pbits) {
     if (gate && !(gate->nonquiet && !gate->converged)) return;
     const uint32_t ctx = blockIdx.x * blockDim.x + threadIdx.x;
     if (ctx >= 65536) return;
     uint32_t c = 0;                                                   // prediction table starts as 0 everywhere (cheetah.rs:53)
-    for (uint32_t r = 0; r < nruns; ++r) {
-        const uint32_t u = u1P_all[(size_t)r * 65536 + ctx];
-        if (!u) continue;
-        const uint32_t i = u - 1;
-        if (in[i] == c) atomicOr(&Pbits[i >> 5], 1u << (i & 31));
-        c = tabP_all[(size_t)r * 65536 + ctx];
+    for (uint32_t r0 = 0; r0 < nruns; r0 += 8) {
+        uint4 e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = (r0 + k < nruns) ? entP_all[(size_t)(r0 + k) * 65536 + ctx] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (e[k].y != epoch) continue;
+            const uint32_t i = e[k].z - 1;
+            if (in[i] == c) atomicOr(&Pbits[i >> 5], 1u << (i & 31));
+            c = e[k].x;
+        }
     }
 }
 
 // ---- pass C: chunk map (MRU-2) on the non-predicted quads -----------------------------------------------------------------
+// Table entry per (run, bucket): {a | b << 16, epoch << 2 | T, 1 + index of the first access, 1 + index of the first access that differs}
+// T: 0 untouched, 1 a known, 2 a and b known.
 __global__ void __launch_bounds__(RP_WARPS * 32)
 chee_pass_c(const uint32_t* __restrict__ in, uint64_t nquads, uint64_t nblocks, const uint8_t* __restrict__ copymap, uint32_t nruns, uint64_t ntiles,
-            const Status* __restrict__ gate, const uint32_t* __restrict__ Pbits, uint32_t* __restrict__ tabC_all, uint32_t* __restrict__ u1C_all,
-            uint32_t* __restrict__ u2C_all, uint8_t* __restrict__ stC_all, uint32_t* __restrict__ Abits, uint32_t* __restrict__ Bbits) {
+            const Status* __restrict__ gate, const uint32_t* __restrict__ Pbits, uint4* __restrict__ entC_all, uint32_t epoch,
+            uint32_t* __restrict__ Abits, uint32_t* __restrict__ Bbits) {
     if (gate && !(gate->nonquiet && !gate->converged)) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (r >= nruns) return;
-    uint32_t* __restrict__ tabC = tabC_all + (size_t)r * 65536;
-    uint32_t* __restrict__ u1C = u1C_all + (size_t)r * 65536;
-    uint32_t* __restrict__ u2C = u2C_all + (size_t)r * 65536;
-    uint8_t* __restrict__ stC = stC_all + (size_t)r * 65536;
+    uint4* __restrict__ entC = entC_all + (size_t)r * 65536;
     const uint64_t b0 = run_block_begin(r, nruns, ntiles);
     uint64_t b1 = run_block_begin(r + 1, nruns, ntiles);
     if (b1 > nblocks) b1 = nblocks;
+    uint32_t qn = (b0 < b1 && b0 * 32 + lane < nquads) ? ld_stream_u32(in + b0 * 32 + lane) : 0u;
+    uint32_t pmn = (b0 < b1) ? __ldcg(&Pbits[b0]) : 0u;
     for (uint64_t b = b0; b < b1; ++b) {
+        const uint32_t q = qn, pm = pmn;
+        if (b + 1 < b1) { qn = ((b + 1) * 32 + lane < nquads) ? ld_stream_u32(in + (b + 1) * 32 + lane) : 0u; pmn = __ldcg(&Pbits[b + 1]); }
         if (copymap && copymap[b]) { if (lane == 0) { Abits[b] = 0; Bbits[b] = 0; } continue; }
         const uint64_t q0 = b * 32;
         const uint32_t nq = (q0 >= nquads) ? 0u : (uint32_t)((nquads - q0 < 32) ? (nquads - q0) : 32);
         if (nq == 0) { if (lane == 0) { Abits[b] = 0; Bbits[b] = 0; } continue; }
-        const uint32_t pm = __ldcg(&Pbits[b]);
         const bool member = lane < nq && !((pm >> lane) & 1u);
-        const uint32_t q = (lane < nq) ? ld_stream_u32(in + q0 + lane) : 0u;
         const uint32_t p = hash_prod(q);
         const uint32_t h = prod_hash(p), v = prod_fp(p, q);
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (member) e = __ldcg(&entC[h]);
         const uint32_t key = member ? h : 0x10000u + lane;
         const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
         const uint32_t lower = grp & lanemask_lt();
         const uint32_t rank = __popc(lower);
         const int src = lower ? 31 - __clz(lower) : (int)lane;
         const uint32_t maxrank = __reduce_max_sync(0xFFFFFFFFu, member ? rank : 0u);
-        // state before my access: first of its group reads the table, the others receive it from their in-warp predecessor
-        uint32_t a = 0, bb = 0, T = 0;
-        if (member && !lower) {
-            T = __ldcg(&stC[h]);
-            if (T) { const uint32_t ab = __ldcg(&tabC[h]); a = ab & 0xFFFFu; bb = ab >> 16; }
-        }
-        uint32_t code = 0;          // 0 plain (or unresolved), 1 MAP_A, 2 MAP_B
-        uint32_t na = 0, nb = 0, nT = 0;
+        // state before my access: the first lane of a group takes it from the table, the others from their in-warp predecessor
+        const bool fresh = (e.y >> 2) == epoch;
+        uint32_t a = fresh ? (e.x & 0xFFFFu) : 0u, bb = fresh ? (e.x >> 16) : 0u, T = fresh ? (e.y & 3u) : 0u;
+        uint32_t u1 = fresh ? e.z : 0u, u2 = fresh ? e.w : 0u;
+        uint32_t code = 0;          // 0 plain (or not yet decidable), 1 MAP_A, 2 MAP_B
+        uint32_t na = 0, nb = 0, nT = 0, nu1 = 0, nu2 = 0;
         for (uint32_t rk = 0; rk <= maxrank; ++rk) {
             if (member && rank == rk) {
-                if (T == 0) {                       // first touch of the bucket in this run: flag decided later from the carry-in
-                    u1C[h] = (uint32_t)(q0 + lane) + 1u;
-                    na = v; nb = 0; nT = 1;
+                nu1 = u1; nu2 = u2;
+                if (T == 0) {                       // first touch of the bucket in this run: decided later from the carry-in
+                    nu1 = (uint32_t)(q0 + lane) + 1u; na = v; nb = 0; nT = 1;
                 } else if (T == 1) {
                     if (v == a) { code = 1; na = a; nb = 0; nT = 1; }
-                    else { u2C[h] = (uint32_t)(q0 + lane) + 1u; na = v; nb = a; nT = 2; }   // MAP_B iff v == (unknown) b: decided later
+                    else { nu2 = (uint32_t)(q0 + lane) + 1u; na = v; nb = a; nT = 2; }        // MAP_B iff v == (unknown) b: decided later
                 } else {
                     if (v == a) { code = 1; na = a; nb = bb; }
                     else { code = (v == bb) ? 2u : 0u; na = v; nb = a; }                       // cheetah.rs:137-142
                     nT = 2;
                 }
             }
-            // hand the state to the next member of each group
             const uint32_t ra = __shfl_sync(0xFFFFFFFFu, na, src), rb = __shfl_sync(0xFFFFFFFFu, nb, src), rT = __shfl_sync(0xFFFFFFFFu, nT, src);
-            if (member && rank == rk + 1) { a = ra; bb = rb; T = rT; }
+            const uint32_t r1 = __shfl_sync(0xFFFFFFFFu, nu1, src), r2 = __shfl_sync(0xFFFFFFFFu, nu2, src);
+            if (member && rank == rk + 1) { a = ra; bb = rb; T = rT; u1 = r1; u2 = r2; }
         }
-        if (member && (grp & lanemask_gt()) == 0) { tabC[h] = na | (nb << 16); stC[h] = (uint8_t)nT; }
+        if (member && (grp & lanemask_gt()) == 0) entC[h] = make_uint4(na | (nb << 16), (epoch << 2) | nT, nu1, nu2);
         const uint32_t am = __ballot_sync(0xFFFFFFFFu, code == 1), bm = __ballot_sync(0xFFFFFFFFu, code == 2);
         if (lane == 0) { Abits[b] = am; Bbits[b] = bm; }
         __syncwarp();
@@ -188,33 +191,36 @@ chee_pass_c(const uint32_t* __restrict__ in, uint64_t nquads, uint64_t nblocks, 
 }
 
 // walk the runs in order per bucket: resolve the (at most two) undecided accesses of each run, carry (a, b) on
-__global__ void chee_fold_c(const uint32_t* __restrict__ in, uint32_t nruns, const Status* __restrict__ gate, const uint32_t* __restrict__ tabC_all,
-                            const uint32_t* __restrict__ u1C_all, const uint32_t* __restrict__ u2C_all, const uint8_t* __restrict__ stC_all,
-                            uint32_t* __restrict__ Abits, uint32_t* __restrict__ Bbits) {
+__global__ void chee_fold_c(const uint32_t* __restrict__ in, uint32_t nruns, const Status* __restrict__ gate, const uint4* __restrict__ entC_all,
+                            uint32_t epoch, uint32_t* __restrict__ Abits, uint32_t* __restrict__ Bbits) {
     if (gate && !(gate->nonquiet && !gate->converged)) return;
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= 65536) return;
     // chunk map starts as (quad 0, quad 0) (cheetah.rs:52): only bucket 0 can ever match that
     uint32_t a0 = h ? FP_INVALID : 0u, b0 = a0;
-    for (uint32_t r = 0; r < nruns; ++r) {
-        const size_t o = (size_t)r * 65536 + h;
-        const uint32_t T = stC_all[o];
-        if (!T) continue;
-        const uint32_t i1 = u1C_all[o] - 1;
-        const uint32_t q1 = in[i1];
-        const uint32_t v1 = prod_fp(hash_prod(q1), q1);
-        uint32_t bafter;
-        if (v1 == a0) { atomicOr(&Abits[i1 >> 5], 1u << (i1 & 31)); bafter = b0; }
-        else { if (v1 == b0) atomicOr(&Bbits[i1 >> 5], 1u << (i1 & 31)); bafter = a0; }
-        if (T == 2) {
-            const uint32_t i2 = u2C_all[o] - 1;
-            const uint32_t q2 = in[i2];
-            const uint32_t v2 = prod_fp(hash_prod(q2), q2);
-            if (v2 == bafter) atomicOr(&Bbits[i2 >> 5], 1u << (i2 & 31));
-            const uint32_t ab = tabC_all[o];
-            a0 = ab & 0xFFFFu; b0 = ab >> 16;
-        } else {                                   // the run accessed the bucket with one value only
-            if (v1 != a0) { b0 = a0; a0 = v1; }
+    for (uint32_t r0 = 0; r0 < nruns; r0 += 8) {
+        uint4 e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = (r0 + k < nruns) ? entC_all[(size_t)(r0 + k) * 65536 + h] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((e[k].y >> 2) != epoch) continue;
+            const uint32_t T = e[k].y & 3u;
+            const uint32_t i1 = e[k].z - 1;
+            const uint32_t q1 = in[i1];
+            const uint32_t v1 = prod_fp(hash_prod(q1), q1);
+            uint32_t bafter;
+            if (v1 == a0) { atomicOr(&Abits[i1 >> 5], 1u << (i1 & 31)); bafter = b0; }
+            else { if (v1 == b0) atomicOr(&Bbits[i1 >> 5], 1u << (i1 & 31)); bafter = a0; }
+            if (T == 2) {
+                const uint32_t i2 = e[k].w - 1;
+                const uint32_t q2 = in[i2];
+                const uint32_t v2 = prod_fp(hash_prod(q2), q2);
+                if (v2 == bafter) atomicOr(&Bbits[i2 >> 5], 1u << (i2 & 31));
+                a0 = e[k].x & 0xFFFFu; b0 = e[k].x >> 16;
+            } else if (v1 != a0) {                  // the run accessed the bucket with one value only
+                b0 = a0; a0 = v1;
+            }
         }
     }
 }
@@ -328,9 +334,10 @@ __global__ void chee_open_gate(Status* __restrict__ st) { st->nonquiet = 1; }   
 using namespace chee;
 
 struct CheeLayout {
-    size_t status, Pbits, Abits, Bbits, copymap, copymap2, incb, seg_state, ctx0, tile_bytes, tile_local, group_total, group_off,
-           tabP, u1P, tabC, u1C, u2C, stC, total;
+    size_t status, status2, Pbits, Abits, Bbits, copymap, copymap2, incb, seg_state, ctx0, tile_bytes, tile_local, group_total, group_off, total;
 };
+
+constexpr uint32_t PREFIX_TILES = 64;           // stage A settles the copy map of the first MiB on its own (cold-dictionary blocks)
 
 static uint32_t chee_pick_runs(size_t nbytes, int num_sms) {
     const uint64_t nblocks = (nbytes + 127) / 128;
@@ -338,6 +345,7 @@ static uint32_t chee_pick_runs(size_t nbytes, int num_sms) {
     uint64_t r = ntiles / 2;                    // >= 32 KiB per run
     const uint64_t cap = (uint64_t)num_sms * 8; // 8 warps (runs) per SM
     if (r > cap) r = cap;
+    if (r < PREFIX_TILES && ntiles >= PREFIX_TILES) r = PREFIX_TILES;
     if (r < 1) r = 1;
     return (uint32_t)r;
 }
@@ -349,6 +357,7 @@ static size_t chee_layout(size_t nbytes, uint32_t nruns, CheeLayout* L) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     L->status = take(sizeof(Status));
+    L->status2 = take(sizeof(Status));
     L->Pbits = take((ntiles * TILE_B + 32) * 4);
     L->Abits = take((ntiles * TILE_B + 32) * 4);
     L->Bbits = take((ntiles * TILE_B + 32) * 4);
@@ -361,13 +370,6 @@ static size_t chee_layout(size_t nbytes, uint32_t nruns, CheeLayout* L) {
     L->tile_local = take((ntiles + 1) * 4);
     L->group_total = take((ngroups + 1) * 8);
     L->group_off = take((ngroups + 1) * 8);
-    // zeroed before every round: u1P and stC (adjacent)
-    L->u1P = take((size_t)nruns * 65536 * 4);
-    L->stC = take((size_t)nruns * 65536);
-    L->tabP = take((size_t)nruns * 65536 * 4);
-    L->tabC = take((size_t)nruns * 65536 * 4);
-    L->u1C = take((size_t)nruns * 65536 * 4);
-    L->u2C = take((size_t)nruns * 65536 * 4);
     L->total = off;
     return off;
 }
@@ -376,48 +378,75 @@ size_t chee_workspace_bytes(size_t nbytes, int num_sms) {
     CheeLayout L;
     return chee_layout(nbytes, chee_pick_runs(nbytes, num_sms), &L);
 }
+// The per-run tables live in a buffer of their own: it must be zero when allocated and only ever be written by these kernels
+// (entries are validated by epoch tags instead of being cleared).
+size_t chee_tables_bytes(size_t nbytes, int num_sms) { return (size_t)chee_pick_runs(nbytes, num_sms) * 65536 * sizeof(uint4) * 2; }
 
 // Enqueue the parallel Cheetah encode. *d_converged (device u32) != 0 afterwards means d_out / d_out_size hold the result; otherwise
-// the caller's in-order kernel (queued behind, gated on that flag) produces it.
-cudaError_t chee_encode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, int num_sms,
-                                 uint64_t* d_out_size, uint32_t* d_converged, cudaStream_t stream, uint64_t* launches) {
+// the caller's in-order kernel (queued behind, gated on that flag) produces it. `epoch_base`: the caller hands out 16 fresh epochs
+// (values in 1 .. 2^30) per call and clears `tables` if it ever has to reuse one.
+cudaError_t chee_encode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, uint8_t* tables, uint32_t epoch_base,
+                                 int num_sms, uint64_t* d_out_size, uint32_t* d_converged, cudaStream_t stream, uint64_t* launches) {
     const uint32_t nruns = chee_pick_runs(nbytes, num_sms);
     CheeLayout L; chee_layout(nbytes, nruns, &L);
-    const uint64_t nquads = nbytes / 4, nblocks = (nbytes + 127) / 128;
+    const uint64_t nblocks = (nbytes + 127) / 128;
     const uint32_t ntiles = (uint32_t)((nblocks + TILE_B - 1) / TILE_B);
     const uint32_t ngroups = (ntiles + 4095) / 4096;
-    Status* st = reinterpret_cast<Status*>(ws + L.status);
+    Status* stA = reinterpret_cast<Status*>(ws + L.status);
+    Status* stB = reinterpret_cast<Status*>(ws + L.status2);
     const uint32_t* in32 = reinterpret_cast<const uint32_t*>(d_in);
     uint32_t* Pb = reinterpret_cast<uint32_t*>(ws + L.Pbits); uint32_t* Ab = reinterpret_cast<uint32_t*>(ws + L.Abits); uint32_t* Bb = reinterpret_cast<uint32_t*>(ws + L.Bbits);
     uint8_t* cm = ws + L.copymap; uint8_t* cm2 = ws + L.copymap2; uint8_t* incb = ws + L.incb;
     uint32_t* seg = reinterpret_cast<uint32_t*>(ws + L.seg_state);
     uint32_t* ctx0 = reinterpret_cast<uint32_t*>(ws + L.ctx0);
-    cudaError_t e = cudaMemsetAsync(st, 0, sizeof(Status), stream);
+    uint32_t* tile_bytes = reinterpret_cast<uint32_t*>(ws + L.tile_bytes);
+    uint4* entP = reinterpret_cast<uint4*>(tables);
+    uint4* entC = entP + (size_t)nruns * 65536;
+    cudaError_t e = cudaMemsetAsync(ws + L.status, 0, L.Pbits - L.status, stream);     // both status blocks
     if (e != cudaSuccess) return e;
-    chee_open_gate<<<1, 1, 0, stream>>>(st); ++*launches;
-    const uint32_t nseg = (uint32_t)((nblocks + 255) / 256);
-    const uint32_t run_ctas = (nruns + RP_WARPS - 1) / RP_WARPS;
-    constexpr int ROUNDS = 5;
-    for (int it = 0; it <= ROUNDS; ++it) {
+
+    // one fixed-point round over the first `nb` bytes cut into `runs` runs: flags under the current map, incompressible bits, automaton
+    auto round = [&](Status* st, int it, size_t nb, uint32_t runs, uint32_t epoch) -> cudaError_t {
+        const uint64_t nq = nb / 4, nblk = (nb + 127) / 128;
+        const uint32_t nt = (uint32_t)((nblk + TILE_B - 1) / TILE_B);
+        const uint32_t nseg = (uint32_t)((nblk + 255) / 256);
+        const uint32_t run_ctas = (runs + RP_WARPS - 1) / RP_WARPS;
         const uint8_t* mask = it ? cm : nullptr;
-        e = cudaMemsetAsync(ws + L.u1P, 0, (L.tabP - L.u1P), stream);     // u1P and stC (the gate cannot skip a memset; it is cheap)
-        if (e != cudaSuccess) return e;
-        chee_ctx0<<<(nruns + 127) / 128, 128, 0, stream>>>(in32, nquads, mask, nruns, ntiles, st, ctx0);
-        chee_pass_p<<<run_ctas, RP_WARPS * 32, 0, stream>>>(in32, nquads, nblocks, mask, nruns, ntiles, st, ctx0,
-                                                            reinterpret_cast<uint32_t*>(ws + L.tabP), reinterpret_cast<uint32_t*>(ws + L.u1P), Pb);
-        chee_fold_p<<<65536 / 128, 128, 0, stream>>>(in32, nruns, st, reinterpret_cast<uint32_t*>(ws + L.tabP), reinterpret_cast<uint32_t*>(ws + L.u1P), Pb);
-        chee_pass_c<<<run_ctas, RP_WARPS * 32, 0, stream>>>(in32, nquads, nblocks, mask, nruns, ntiles, st, Pb, reinterpret_cast<uint32_t*>(ws + L.tabC),
-                                                            reinterpret_cast<uint32_t*>(ws + L.u1C), reinterpret_cast<uint32_t*>(ws + L.u2C), ws + L.stC, Ab, Bb);
-        chee_fold_c<<<65536 / 128, 128, 0, stream>>>(in32, nruns, st, reinterpret_cast<uint32_t*>(ws + L.tabC), reinterpret_cast<uint32_t*>(ws + L.u1C),
-                                                     reinterpret_cast<uint32_t*>(ws + L.u2C), ws + L.stC, Ab, Bb);
-        chee_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, mask, nbytes, nblocks, ntiles, 0, st, incb, reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
-        e = prot_iterate_launch(nullptr, nbytes, nblocks, nseg, st, it, incb, cm, cm2, seg, seg + (nseg + 1), 128, num_sms, stream);
-        if (e != cudaSuccess) return e;
+        chee_ctx0<<<(runs + 127) / 128, 128, 0, stream>>>(in32, nq, mask, runs, nt, st, ctx0);
+        chee_pass_p<<<run_ctas, RP_WARPS * 32, 0, stream>>>(in32, nq, nblk, mask, runs, nt, st, ctx0, entP, epoch, Pb);
+        chee_fold_p<<<65536 / 128, 128, 0, stream>>>(in32, runs, st, entP, epoch, Pb);
+        chee_pass_c<<<run_ctas, RP_WARPS * 32, 0, stream>>>(in32, nq, nblk, mask, runs, nt, st, Pb, entC, epoch, Ab, Bb);
+        chee_fold_c<<<65536 / 128, 128, 0, stream>>>(in32, runs, st, entC, epoch, Ab, Bb);
+        chee_tile_sizes<<<(nt + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, mask, nb, nblk, nt, 0, st, incb, tile_bytes);
         *launches += 7;
+        return prot_iterate_launch(nullptr, nb, nblk, nseg, st, it, incb, cm, cm2, seg, seg + (nseg + 1), 128, num_sms, stream);
+    };
+
+    Status* st = stA;
+    int first_it = 0;
+    chee_open_gate<<<1, 1, 0, stream>>>(stA); ++*launches;
+    if (ntiles > 2 * PREFIX_TILES) {
+        // Stage A: a cold dictionary makes the first blocks incompressible on every input, and settling that takes ~4 rounds: run
+        // them on the first MiB alone (the copy map of a prefix does not depend on what follows). Stage B then starts from that map
+        // and normally confirms it in one round over the whole input.
+        const size_t nbA = (size_t)PREFIX_TILES * TILE_B * 128;
+        e = cudaMemsetAsync(cm, 0, (size_t)ntiles * TILE_B, stream);
+        if (e != cudaSuccess) return e;
+        for (int it = 0; it <= 6; ++it) {
+            e = round(stA, it, nbA, PREFIX_TILES, epoch_base + (uint32_t)it);
+            if (e != cudaSuccess) return e;
+        }
+        chee_open_gate<<<1, 1, 0, stream>>>(stB); ++*launches;
+        st = stB;
+        first_it = 1;
+    }
+    for (int it = first_it; it <= 7; ++it) {
+        e = round(st, it, nbytes, nruns, epoch_base + 8u + (uint32_t)it);
+        if (e != cudaSuccess) return e;
     }
     // final sizes under the committed copy map (valid only if converged), scan, emit
-    chee_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, cm, nbytes, nblocks, ntiles, 1, st, incb, reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
-    e = scan_tiles_launch(reinterpret_cast<uint32_t*>(ws + L.tile_bytes), ntiles, reinterpret_cast<uint32_t*>(ws + L.tile_local),
+    chee_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, cm, nbytes, nblocks, ntiles, 1, st, incb, tile_bytes);
+    e = scan_tiles_launch(tile_bytes, ntiles, reinterpret_cast<uint32_t*>(ws + L.tile_local),
                           reinterpret_cast<uint64_t*>(ws + L.group_total), reinterpret_cast<uint64_t*>(ws + L.group_off), ngroups, st, cap, d_out_size, stream);
     if (e != cudaSuccess) return e;
     chee_emit<<<ntiles, 256, 0, stream>>>(in32, nbytes, nblocks, Pb, Ab, Bb, cm, st, reinterpret_cast<uint32_t*>(ws + L.tile_local),

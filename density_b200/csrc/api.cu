@@ -51,7 +51,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;     // for the synchronous host-pointer entry points (compute)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the pipelined host path
     DevBuf ws, stage_in, stage_out, pipe_tables;
-    DevBuf chee_tables;                // epoch-tagged run tables of the Cheetah encoder (zero at allocation, never shared)
+    DevBuf chee_tables[2][3];          // epoch-tagged run tables of the Cheetah / Lion encoders (zero at allocation, one entry format each)
     uint32_t chee_epoch = 0;
     uint64_t* h_sizes = nullptr;       // pinned, PIPE_MAX_CHUNKS entries
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
@@ -137,22 +137,25 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
             if (ev != nullptr && e == cudaSuccess) c->prof_count++;
         }
         c->last_was_chameleon_fastpath_capable = (path != 2);
-    } else if (alg == ALG_CHEETAH && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 3) && !(reinterpret_cast<uintptr_t>(d_out) & 1)) {
-        // run-parallel Cheetah encoder; the exact in-order kernel is queued behind it and only runs if the copy map did not settle
+    } else if ((alg == ALG_CHEETAH || alg == ALG_LION) && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 3) && !(reinterpret_cast<uintptr_t>(d_out) & 1)) {
+        // run-parallel Cheetah / Lion encoder; the exact in-order kernel is queued behind it and only runs if the copy map did not settle
         const size_t pw = (chee_workspace_bytes(n, c->num_sms) + 255) & ~(size_t)255;
         e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg));
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
-        if (e == cudaSuccess) e = c->chee_tables.ensure(chee_tables_bytes(n, c->num_sms));
+        DevBuf* tb = c->chee_tables[alg == ALG_LION];
+        for (int rg = 0; rg < 3 && e == cudaSuccess; ++rg) e = tb[rg].ensure(chee_tables_bytes(alg, rg, n, c->num_sms) + 256);
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
-        if (c->chee_epoch > 0x3FFFFF00u) {                 // epochs exhausted (2^26 calls): start over on cleared tables
-            e = cudaMemsetAsync(c->chee_tables.p, 0, c->chee_tables.bytes, stream);
+        if (c->chee_epoch > 0x0FFFFF00u) {                 // epochs exhausted (2^23 calls): start over on cleared tables
+            for (int a2 = 0; a2 < 2; ++a2) for (int rg = 0; rg < 3; ++rg)
+                if (c->chee_tables[a2][rg].p) { e = cudaMemsetAsync(c->chee_tables[a2][rg].p, 0, c->chee_tables[a2][rg].bytes, stream); if (e != cudaSuccess) break; }
             if (e != cudaSuccess) { set_error("cudaMemsetAsync", e); return DENSITY_B200_ECUDA; }
             c->chee_epoch = 0;
         }
         const uint32_t epoch_base = c->chee_epoch + 1;
-        c->chee_epoch += 16;
+        c->chee_epoch += 32;
         uint32_t* d_conv = reinterpret_cast<uint32_t*>(c->ws.p + pw);
-        e = chee_encode_parallel(d_in, n, d_out, cap, c->ws.p, c->chee_tables.p, epoch_base, c->num_sms, d_out_size, d_conv, stream, &launches);
+        uint8_t* const tabs[3] = {tb[0].p, tb[1].p, tb[2].p};
+        e = chee_encode_parallel(alg, d_in, n, d_out, cap, c->ws.p, tabs, epoch_base, c->num_sms, d_out_size, d_conv, stream, &launches);
         if (e == cudaSuccess && path != 1)
             e = scalar_encode(alg, d_in, n, d_out, cap, c->ws.p + pw + 256, d_out_size, stream, &launches, d_conv);
         c->last_was_chameleon_fastpath_capable = 0;
@@ -499,7 +502,8 @@ void density_b200_shutdown(void) {
         DeviceCtx& c = g_ctx[d];
         if (!c.ready) continue;
         cudaSetDevice(d);
-        c.ws.release(); c.stage_in.release(); c.stage_out.release(); c.chee_tables.release(); c.chee_epoch = 0;
+        c.ws.release(); c.stage_in.release(); c.stage_out.release(); for (int a2 = 0; a2 < 2; ++a2) for (int rg = 0; rg < 3; ++rg) c.chee_tables[a2][rg].release();
+        c.chee_epoch = 0;
         if (c.d_size) cudaFree(c.d_size);
         if (c.h_size) cudaFreeHost(c.h_size);
         if (c.stream) cudaStreamDestroy(c.stream);

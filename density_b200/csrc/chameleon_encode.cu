@@ -1057,7 +1057,9 @@ cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint3
 cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* st, int it, uint8_t* inc,
                                 uint8_t* cm_old, uint8_t* cm_new, uint32_t* in_state, uint32_t* out_state, int /*block_bytes*/, int num_sms,
                                 cudaStream_t stream) {
-    prot_iterate<<<num_sms > 0 ? num_sms : 1, PI_THREADS, 0, stream>>>(sigw_or_null, nbytes, nblocks, nseg, st, it, inc, cm_old, cm_new, in_state, out_state);
+    int ctas = num_sms > 0 ? num_sms : 1;
+    if ((uint32_t)ctas > nseg) ctas = nseg ? (int)nseg : 1;       // small inputs: cheaper grid barriers
+    prot_iterate<<<ctas, PI_THREADS, 0, stream>>>(sigw_or_null, nbytes, nblocks, nseg, st, it, inc, cm_old, cm_new, in_state, out_state);
     return cudaGetLastError();
 }
 cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint32_t* tile_local, uint64_t* group_total, uint64_t* group_off,

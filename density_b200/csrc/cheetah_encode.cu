@@ -619,14 +619,15 @@ __global__ void chee_finish(const Status* __restrict__ st, uint32_t* __restrict_
     *d_converged = st->converged;
     if (!st->converged && d_out_size) *d_out_size = 0;
 }
-__global__ void chee_open_gate(Status* __restrict__ st) { st->nonquiet = 1; }   // Cheetah always runs the copy-map iteration
+// open the gate of a stage of up to 8 rounds; a continuation stage inherits "already settled" from the stage before it
+__global__ void chee_chain_gate(Status* __restrict__ st, const Status* __restrict__ prev) { st->nonquiet = 1; st->converged = prev ? prev->converged : 0u; }   // Cheetah always runs the copy-map iteration
 
 }  // namespace chee
 
 using namespace chee;
 
 struct CheeLayout {
-    size_t status, status2, Pbits, Abits, Bbits, F0, F1, F2, copymap, copymap2, incb, seg_state, ctx0, tile_bytes, tile_local, group_total, group_off, total;
+    size_t status, Pbits, Abits, Bbits, F0, F1, F2, copymap, copymap2, incb, seg_state, ctx0, tile_bytes, tile_local, group_total, group_off, total;
 };
 
 constexpr uint32_t PREFIX_TILES = 64;           // stage A settles the copy map of the first MiB on its own (cold-dictionary blocks)
@@ -649,8 +650,7 @@ static size_t chee_layout(size_t nbytes, uint32_t nruns, CheeLayout* L) {
     const uint64_t maxblocks = ntiles * TILE_B * 2;          // Lion: two 64-byte blocks per step
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    L->status = take(sizeof(Status));
-    L->status2 = take(sizeof(Status));
+    L->status = take(4 * sizeof(Status));          // one per stage of the copy-map iteration (8 rounds each)
     L->Pbits = take((ntiles * TILE_B + 32) * 4);
     L->Abits = take((ntiles * TILE_B + 32) * 4);
     L->Bbits = take((ntiles * TILE_B + 32) * 4);
@@ -696,8 +696,7 @@ cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, ui
     const uint64_t nblocks = (nbytes + bbytes - 1) / bbytes;
     const uint32_t ntiles = (uint32_t)(((nbytes + 127) / 128 + TILE_B - 1) / TILE_B);
     const uint32_t ngroups = (ntiles + 4095) / 4096;
-    Status* stA = reinterpret_cast<Status*>(ws + L.status);
-    Status* stB = reinterpret_cast<Status*>(ws + L.status2);
+    Status* const stages = reinterpret_cast<Status*>(ws + L.status);
     const uint32_t* in32 = reinterpret_cast<const uint32_t*>(d_in);
     uint32_t* Pb = reinterpret_cast<uint32_t*>(ws + L.Pbits); uint32_t* Ab = reinterpret_cast<uint32_t*>(ws + L.Abits); uint32_t* Bb = reinterpret_cast<uint32_t*>(ws + L.Bbits);
     uint32_t* F0 = reinterpret_cast<uint32_t*>(ws + L.F0); uint32_t* F1 = reinterpret_cast<uint32_t*>(ws + L.F1); uint32_t* F2 = reinterpret_cast<uint32_t*>(ws + L.F2);
@@ -737,28 +736,35 @@ cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, ui
         return prot_iterate_launch(nullptr, nb, nblk, nseg, st, it, incb, cm, cm2, seg, seg + (nseg + 1), (int)bbytes, num_sms, stream);
     };
 
-    Status* st = stA;
-    int first_it = 0;
-    chee_open_gate<<<1, 1, 0, stream>>>(stA); ++*launches;
+    // A stage = up to 8 rounds on one Status block (prot_iterate owns 8 grid-barrier slots per block).
+    auto stage = [&](Status* st, const Status* inherit, int first_it, size_t nb, uint32_t runs, uint32_t ep0) -> cudaError_t {
+        chee_chain_gate<<<1, 1, 0, stream>>>(st, inherit); ++*launches;
+        for (int it = first_it; it <= 7; ++it) {
+            cudaError_t err = round(st, it, nb, runs, ep0 + (uint32_t)it);
+            if (err != cudaSuccess) return err;
+        }
+        return cudaSuccess;
+    };
+    Status* st;
     if (ntiles > 2 * PREFIX_TILES) {
-        // Stage A: a cold dictionary makes the first blocks incompressible on every input, and settling that takes 4-7 rounds: run
-        // them on the first MiB alone (the copy map of a prefix does not depend on what follows). Stage B then starts from that map
-        // and normally confirms it in one round over the whole input.
+        // Stages A1, A2: a cold dictionary makes the first blocks incompressible on every input, and settling that takes 4-10 rounds
+        // (copied blocks perturb the sizes of their near-threshold neighbours): run them on the first MiB alone (the copy map of a
+        // prefix does not depend on what follows). Stages B1, B2 then start from that map and normally confirm it in one round
+        // over the whole input.
         const size_t nbA = (size_t)PREFIX_TILES * TILE_B * 128;
         e = cudaMemsetAsync(cm, 0, (size_t)ntiles * TILE_B * 2, stream);
         if (e != cudaSuccess) return e;
-        for (int it = 0; it <= 7; ++it) {
-            e = round(stA, it, nbA, PREFIX_TILES, epoch_base + (uint32_t)it);
-            if (e != cudaSuccess) return e;
-        }
-        chee_open_gate<<<1, 1, 0, stream>>>(stB); ++*launches;
-        st = stB;
-        first_it = 1;
+        e = stage(&stages[0], nullptr, 0, nbA, PREFIX_TILES, epoch_base);
+        if (e == cudaSuccess) e = stage(&stages[1], &stages[0], 1, nbA, PREFIX_TILES, epoch_base + 8);
+        if (e == cudaSuccess) e = stage(&stages[2], nullptr, 1, nbytes, nruns, epoch_base + 16);
+        if (e == cudaSuccess) e = stage(&stages[3], &stages[2], 1, nbytes, nruns, epoch_base + 24);
+        st = &stages[3];
+    } else {
+        e = stage(&stages[0], nullptr, 0, nbytes, nruns, epoch_base);
+        if (e == cudaSuccess) e = stage(&stages[1], &stages[0], 1, nbytes, nruns, epoch_base + 8);
+        st = &stages[1];
     }
-    for (int it = first_it; it <= 7; ++it) {
-        e = round(st, it, nbytes, nruns, epoch_base + 8u + (uint32_t)it);
-        if (e != cudaSuccess) return e;
-    }
+    if (e != cudaSuccess) return e;
     // final sizes under the committed copy map (valid only if converged), scan, emit
     if (lion) lion_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, cm, nbytes, nblocks, ntiles, 1, st, incb, tile_bytes);
     else chee_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, cm, nbytes, nblocks, ntiles, 1, st, incb, tile_bytes);

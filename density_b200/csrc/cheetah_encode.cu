@@ -21,6 +21,7 @@
 // first touch, and the first access that differs from it). One fold kernel per table then walks the runs in order per
 // context / bucket, resolves those accesses and carries the state on. Pass P (predictions) must be completely resolved before
 // pass C (chunk map) starts, because only non-predicted quads take part in it.
+#include <stdlib.h>
 #include "common.cuh"
 #include "encode_internal.cuh"
 
@@ -636,7 +637,8 @@ static uint32_t chee_pick_runs(size_t nbytes, int num_sms) {
     const uint64_t nsteps = (nbytes + 127) / 128;
     const uint64_t ntiles = (nsteps + TILE_B - 1) / TILE_B;
     uint64_t r = ntiles / 2;                    // >= 32 KiB per run
-    const uint64_t cap = (uint64_t)num_sms * 8; // 8 warps (runs) per SM
+    static const int per_sm = [] { const char* v = getenv("DENSITY_B200_RUNS_PER_SM"); int k = v ? atoi(v) : 0; return (k >= 1 && k <= 64) ? k : 8; }();
+    const uint64_t cap = (uint64_t)num_sms * per_sm; // warps (runs) per SM: 8 by default (tuning knob; the result does not depend on it)
     if (r > cap) r = cap;
     if (r < PREFIX_TILES && ntiles >= PREFIX_TILES) r = PREFIX_TILES;
     if (r < 1) r = 1;

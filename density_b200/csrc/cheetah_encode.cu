@@ -1,8 +1,8 @@
-// cheetah_encode.cu — run-parallel Cheetah encode for sm_100a.
+// cheetah_encode.cu — run-parallel Cheetah and Lion encode for sm_100a (the Lion kernels start at "Lion (lion.rs:209-271)").
 //
-// Replaces /root/reference/src/algorithms/cheetah/cheetah.rs:121-150 (encode_quad) driven by
-// /root/reference/src/codec/codec.rs:34-80, bit-exactly. Decomposition (validated against the oracle by
-// tools/proto_cheetah_runs.py):
+// Replaces /root/reference/src/algorithms/cheetah/cheetah.rs:121-150 and lion/lion.rs:209-271 (encode_quad) driven by
+// /root/reference/src/codec/codec.rs:34-80, bit-exactly. Cheetah's decomposition (validated against the oracle by
+// tools/proto_cheetah_runs.py; Lion's differs in step 1 only, see below and tools/proto_lion_runs.py):
 //
 //  1. PREDICTED_i <=> quad_i == the quad that followed the previous occurrence of the same CONTEXT, where the context is the
 //     hash of the previous *encoded* quad (0 at the stream start) and the prediction table starts as "0 everywhere"
@@ -14,9 +14,9 @@
 //     of  M -> automaton(incompressible bits under M)  (prot_iterate, shared with the Chameleon encoder). Cheetah needs the
 //     iteration on every input: a cold dictionary makes the first blocks incompressible (11 copied blocks on dickens).
 //
-// Parallelisation: the stream is cut into R contiguous runs (thousands), ONE WARP PER RUN walks its run block by block
-// (a Cheetah block is 32 quads = one quad per lane), with the run's tables in global memory (L2/HBM resident; 768 KiB do not fit
-// an SM). In-warp predecessors come from __match_any_sync; what a run cannot know — the tables carried in from earlier runs —
+// Parallelisation: the stream is cut into R contiguous runs (up to 8 per SM), ONE WARP PER RUN walks its run 32 quads at a time
+// (one Cheetah block = one quad per lane), with the run's tables in global memory (768 KiB do not fit an SM) as epoch-tagged
+// 16-byte entries: an entry whose tag is not the current round's counts as untouched, so the tables are never cleared. In-warp predecessors come from __match_any_sync; what a run cannot know — the tables carried in from earlier runs —
 // is left "unresolved": per run and context at most one PREDICTED decision, per run and bucket at most two map decisions (the
 // first touch, and the first access that differs from it). One fold kernel per table then walks the runs in order per
 // context / bucket, resolves those accesses and carries the state on. Pass P (predictions) must be completely resolved before

@@ -76,10 +76,12 @@ DENSITY_B200_API size_t lion_safe_encode_buffer_size(size_t size);
  */
 DENSITY_B200_API int density_b200_encode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                uint64_t* d_out_size, void* stream);
-/* Test/diagnostic variant: choose the Chameleon encode path explicitly.
-   path 0 = auto (segment-parallel fast path, exact protection-aware fallback when needed),
+/* Test/diagnostic variant: choose the encode path explicitly.
+   Chameleon: path 0 = auto (run-parallel fast path, exact protection-aware fallback when needed),
    1 = fast path only (no fallback; out size is only valid if the stream is "quiet"),
-   2 = exact in-order protection-aware walk only, 3 = scalar reference kernel. */
+   2 = exact in-order protection-aware walk only, 3 = in-order single-thread kernel.
+   Cheetah / Lion: 0 = auto (run-parallel encoder; the in-order kernel, queued behind it, runs only if the copy map did
+   not settle), 1 = run-parallel encoder only (*d_out_size == 0 if the copy map did not settle), 3 = in-order kernel. */
 DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                     uint64_t* d_out_size, void* stream, int path);
 /* Decode counterpart: path 0 = auto (parallel Chameleon decoder, exact in-order kernel when the stream has copy-mode

@@ -325,6 +325,20 @@ using namespace dns;
 
 extern "C" {
 
+/* diagnostic: the device-side status block of the last parallel Chameleon decode on the current device (synchronises) */
+int density_b200_decode_status(uint64_t* out10) {
+    DeviceCtx* c = current_ctx();
+    if (!c || !c->ws.p) return DENSITY_B200_EARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    unsigned char raw[64] = {0};
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(raw, c->ws.p, sizeof(raw), cudaMemcpyDeviceToHost) != cudaSuccess) return DENSITY_B200_ECUDA;
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(raw);
+    const unsigned int* w = reinterpret_cast<const unsigned int*>(raw + 24);
+    out10[0] = q[0]; out10[1] = q[1]; out10[2] = q[2];               // out_bytes, main_blocks, tail_off
+    for (int k = 0; k < 7; ++k) out10[3 + k] = w[k];                 // nonquiet, error, last_main_inc, seq, ps_penalty, ps_start, ps_prev
+    return DENSITY_B200_OK;
+}
+
 size_t chameleon_encode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(true, ALG_CHAMELEON, i, n, o, c); }
 size_t chameleon_decode(const uint8_t* i, size_t n, uint8_t* o, size_t c) { return run_sync(false, ALG_CHAMELEON, i, n, o, c); }
 size_t chameleon_safe_encode_buffer_size(size_t s) { return safe_size(ALG_CHAMELEON, s); }

@@ -14,7 +14,10 @@
 //     index; `dec_block_offsets` re-walks each chunk from its true entry and writes one offset per block.
 //  2. Protection.  `dec_quiet_check`: if no two consecutive blocks are incompressible (>= 256 bytes consumed, codec.rs:98)
 //     the automaton never leaves its initial state and no block is in copy mode (same argument as the encoder). Otherwise
-//     the caller falls back to the exact in-order kernel (scalar_codec.cu).
+//     the candidate walks are void (a copy-mode block has no signature) and `dec_seq_walk` redoes the boundaries in order
+//     with the exact automaton: one warp streams the signatures through shared-memory windows (a block costs ~50 cycles
+//     instead of a dependent DRAM access) and marks the copy-mode blocks; the dictionary passes below then run unchanged
+//     (a copy-mode block is 64 raw quads that neither read nor write the dictionary, codec.rs:89-92).
 //  3. Dictionary.  `cham_decode_pass`: one persistent CTA per contiguous run of blocks, the run's dictionary in shared
 //     memory as 16-bit fingerprints (common.cuh). Per tile of 4096 quads: PLAIN quads (~8 %) are the writers, MAP quads the
 //     readers; barrier-phased optimistic protocol — A readers read / B writers publish / C readers re-read; unchanged means
@@ -39,9 +42,11 @@ struct DecStatus {
     unsigned long long out_bytes;
     unsigned long long main_blocks;      // blocks decoded by the parallel main loop (codec.rs:88-100)
     unsigned long long tail_off;         // stream offset where the tail loop starts
-    unsigned int nonquiet, error;
-    unsigned int last_main_inc, pad;
+    unsigned int nonquiet, error;        // nonquiet bit 0: copy-mode blocks present (cleared again by dec_seq_walk); bit 1: pathological tile
+    unsigned int last_main_inc, seq;     // seq: the boundaries come from dec_seq_walk, automaton state below is valid
+    unsigned int ps_penalty, ps_start, ps_prev, pad;   // protection state after the main loop (protection_state.rs:9-16)
 };
+constexpr unsigned long long BLK_COPY = 1ull << 63;   // blk_off flag: copy-mode block (raw 256 bytes, no signature)
 
 __device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
 
@@ -159,13 +164,79 @@ __global__ void dec_quiet_check(const uint8_t* __restrict__ in, const uint64_t* 
     }
 }
 
+// ---- 2b. in-order boundary walk for streams with copy-mode blocks (codec.rs:88-100 with protection_state.rs) ---------------------
+// The stream is cut into fixed 16 KiB windows; window k (plus the bytes a block starting at its end can reach) is staged in shared
+// memory by the loader warps while thread 0 still walks window k-1, so the walk never waits for DRAM: ~50 cycles per block.
+constexpr int SW_WIN = 16384;
+constexpr int SW_LOAD = SW_WIN + 16;         // + the 8 signature bytes of a block starting at the window's last byte, rounded up to 16
+constexpr int SW_THREADS = 160;              // warp 0 walks, warps 1-4 load
+constexpr int SW_PER = (SW_LOAD / 16 + 127) / 128;   // 16-byte pieces per loader thread
+__device__ __forceinline__ uint4 sw_load16(const uint8_t* __restrict__ in, uint64_t g, uint64_t n, bool al16) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (al16 && g + 16 <= n) return *reinterpret_cast<const uint4*>(in + g);
+    uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
+    for (int k = 0; k < 16; ++k) if (g + k < n) vb[k] = in[g + k];
+    return v;
+}
+__global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __restrict__ in, uint64_t n, uint64_t cap, uint64_t* __restrict__ blk_off,
+                                                           DecStatus* __restrict__ st) {
+    if (!(st->nonquiet & 1u)) return;
+    __shared__ __align__(16) uint8_t win[2][SW_LOAD];
+    const uint32_t tid = threadIdx.x;
+    const bool al16 = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    const uint64_t nwin = (n + SW_WIN - 1) / SW_WIN;
+    Protection ps; ps.init();
+    uint64_t idx = 0, b = 0;
+    // prologue: window 0
+    if (tid >= 32)
+        for (uint32_t i = (tid - 32) * 16; i < (uint32_t)SW_LOAD; i += 128 * 16) *reinterpret_cast<uint4*>(win[0] + i) = sw_load16(in, i, n, al16);
+    __syncthreads();
+    for (uint64_t k = 0; k < nwin; ++k) {
+        const uint64_t wbase = k * SW_WIN;
+        if (tid >= 32) {                                   // loaders: window k+1 into the other buffer (all loads in flight before the stores)
+            uint4 v[SW_PER];
+            const uint64_t nb = wbase + SW_WIN;
+#pragma unroll
+            for (int t = 0; t < SW_PER; ++t) {
+                const uint32_t i = ((tid - 32) + t * 128) * 16;
+                v[t] = (k + 1 < nwin && i < (uint32_t)SW_LOAD) ? sw_load16(in, nb + i, n, al16) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int t = 0; t < SW_PER; ++t) {
+                const uint32_t i = ((tid - 32) + t * 128) * 16;
+                if (i < (uint32_t)SW_LOAD) *reinterpret_cast<uint4*>(win[(k + 1) & 1] + i) = v[t];
+            }
+        } else if (tid == 0) {                             // walker: every block that STARTS inside window k
+            const uint8_t* w = win[k & 1];
+            const uint64_t wend = wbase + SW_WIN;
+            while (idx < wend && n - idx >= 264) {
+                if (ps.revert_to_copy()) {                                  // codec.rs:89-92
+                    blk_off[b++] = idx | BLK_COPY; idx += 256; ps.decay();
+                } else {
+                    const uint8_t* p = w + (idx - wbase);
+                    const uint32_t hits = __popc(ldu16(p) | (ldu16(p + 2) << 16)) + __popc(ldu16(p + 4) | (ldu16(p + 6) << 16));
+                    const uint32_t consumed = 264 - 2 * hits;
+                    blk_off[b++] = idx; idx += consumed; ps.update(consumed >= 256);   // codec.rs:94-98
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        st->main_blocks = b; st->tail_off = idx;
+        st->ps_penalty = ps.copy_penalty; st->ps_start = ps.copy_penalty_start; st->ps_prev = ps.previous_incompressible;
+        st->seq = 1;
+        st->error = (b * 256 > cap) ? 2u : 0u;     // the candidate walk's block count was void
+        st->nonquiet &= ~1u;
+    }
+}
+
 // ---- 3. decode pass ---------------------------------------------------------------------------------------------------------
 constexpr int DP_THREADS = 1024;
 constexpr int DP_QPT = 4;
 constexpr int TILE_Q = DP_THREADS * DP_QPT;   // 4096 quads = 64 blocks
 constexpr int SIDE_N = 4096;
 constexpr uint32_t SIDE_EMPTY = 0xFFFFFFFFu;
-constexpr int SUS_CAP = 2048;      // suspect readers per tile (readers whose bucket is written in this tile); more -> in-order fallback
 
 // writer record: x = hash | fp << 16, y = pos(12) | agree-flag etc.   suspect reader record: x = hash | w << 16, y = pos | touched << 12 | fa << 16
 constexpr uint32_t W_CONF = 1u << 12;
@@ -177,11 +248,12 @@ struct DecSmem {
     uint32_t conf[2048];          // per-tile: writers of the bucket disagree
     uint32_t wbit[2048];          // per-tile: bucket has a writer in this tile
     uint32_t side[SIDE_N];        // per-tile min over writers of (pos << 16 | hash)
-    uint2 wrec[TILE_Q];           // writers (plain quads) of the tile
-    uint2 srec[SUS_CAP];          // suspect readers
+    uint2 wrec[TILE_Q];           // writers (plain quads) of the tile from the front; suspect readers (readers whose bucket is written in
+                                  // this tile) from the back: a quad is one or the other, so the two lists never meet
     unsigned long long boff[2][64];  // stream offset of each block of the tile (double buffered: next tile staged early)
     uint32_t bsig[2][128];           // signature halves
-    uint32_t nw, ns, overflow;
+    uint32_t bcopy[2][2];            // copy-mode blocks of the tile (bit per block)
+    uint32_t nw, ns;
 };
 static_assert(sizeof(DecSmem) <= 227 * 1024, "decode pass shared memory");
 
@@ -194,14 +266,21 @@ __device__ __forceinline__ bool bit_test(const uint32_t* bm, uint32_t i) { retur
 __device__ __forceinline__ void stage_tile(DecSmem& S, int buf, const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off,
                                            uint64_t b0, uint64_t nblocks) {
     const uint32_t tid = threadIdx.x;
-    if (tid < 64) {
-        unsigned long long o = 0; uint32_t lo = 0, hi = 0;
+    if (tid < 64) {     // warps 0 and 1, whole warps
+        unsigned long long o = 0; uint32_t lo = 0, hi = 0; bool copied = false;
         if (b0 + tid < nblocks) {
             o = blk_off[b0 + tid];
-            const uint8_t* p = in + o;
-            lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
+            copied = (o & BLK_COPY) != 0;
+            o &= ~BLK_COPY;
+            if (!copied) {
+                const uint8_t* p = in + o;
+                lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
+                o += 8;                       // payload starts behind the signature
+            }                                 // copy-mode block: 64 raw quads = "all PLAIN" payload right at the block start
         }
         S.boff[buf][tid] = o; S.bsig[buf][2 * tid] = lo; S.bsig[buf][2 * tid + 1] = hi;
+        const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, copied);
+        if ((tid & 31) == 0) S.bcopy[buf][tid >> 5] = cmask;
     }
 }
 // Issue the payload loads of my DP_QPT quads of the tile staged in `buf`: MAP -> 16-bit hash, PLAIN -> the quad.
@@ -217,7 +296,7 @@ __device__ __forceinline__ void fetch_payload(const DecSmem& S, int buf, const u
             const uint32_t lo = S.bsig[buf][2 * bl], hi = S.bsig[buf][2 * bl + 1];
             const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
             const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
-            const uint8_t* p = in + S.boff[buf][bl] + 8 + 4 * k - 2 * before;
+            const uint8_t* p = in + S.boff[buf][bl] + 4 * k - 2 * before;
             if (flag) { if (!WONLY) v[j] = ldu16(p); }                       // decode_map reads the 16-bit hash (chameleon.rs:64)
             else v[j] = ldu16(p) | (ldu16(p + 2) << 16);                     // decode_plain reads the quad (chameleon.rs:56)
         }
@@ -255,7 +334,7 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
             }
         }
         for (uint32_t i = tid; i < SIDE_N; i += DP_THREADS) S.side[i] = SIDE_EMPTY;
-        if (tid == 0) { S.nw = 0; S.ns = 0; S.overflow = 0; }
+        if (tid == 0) { S.nw = 0; S.ns = 0; }
     }
     __syncthreads();
 
@@ -275,7 +354,7 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
         // ---- phase A: my quads (prefetched); writers compact themselves; readers read the pre-tile dictionary ----------
         uint32_t val[DP_QPT];       // PLAIN: the quad; MAP: hash from the stream
         uint32_t fa[DP_QPT];        // readers: pre-tile fingerprint
-        uint32_t kind = 0;          // per sub-row: bit j = active, bit 4+j = writer, bit 8+j = reader bucket touched pre-tile
+        uint32_t kind = 0;          // per sub-row: bit j = active, bit 4+j = writer, bit 8+j = reader bucket touched pre-tile, bit 12+j = raw (copy mode)
         uint32_t wb[DP_QPT], wtot = 0;
 #pragma unroll
         for (int j = 0; j < DP_QPT; ++j) {
@@ -284,7 +363,9 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
             val[j] = nval[j]; fa[j] = 0;
             if (active) {
                 const uint32_t flag = (S.bsig[cur][2 * bl + (j & 1)] >> lane) & 1u;
-                if (flag) {
+                if ((S.bcopy[cur][bl >> 5] >> (bl & 31)) & 1u) {
+                    kind |= 1u << (12 + j);             // raw quad of a copy-mode block: no dictionary access at all
+                } else if (flag) {
                     if (!WONLY) {
                         fa[j] = S.tab[val[j]];
                         if (fa[j] != 0 || bit_test(S.vbit, val[j])) kind |= 1u << (8 + j);
@@ -337,7 +418,7 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
                 const bool touched = kind & (1u << (8 + j));
                 bool suspect = false;
                 if (active) {
-                    if (writer) {
+                    if (writer || (kind & (1u << (12 + j)))) {
                         out[q0 + pos] = val[j];
                     } else if (!bit_test(S.wbit, val[j])) {
                         // no PLAIN quad of this tile falls into my bucket: the pre-tile dictionary decides (empty -> 0, chameleon.rs:41)
@@ -353,8 +434,7 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
                     base = __shfl_sync(0xFFFFFFFFu, base, 0);
                     if (suspect) {
                         const uint32_t e = base + __popc(sm & lanemask_lt());
-                        if (e < SUS_CAP) S.srec[e] = make_uint2(val[j], pos | (touched ? S_TOUCHED : 0u) | (fa[j] << 16));
-                        else S.overflow = 1;
+                        S.wrec[TILE_Q - 1 - e] = make_uint2(val[j], pos | (touched ? S_TOUCHED : 0u) | (fa[j] << 16));
                     }
                 }
             }
@@ -370,7 +450,7 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
             }
         }
         __syncthreads();  // S3
-        const uint32_t ns = S.ns < (uint32_t)SUS_CAP ? S.ns : (uint32_t)SUS_CAP;
+        const uint32_t ns = S.ns;
 
         // ---- phase D: suspect readers resolve; writers of disagreeing buckets leave the last value ----------------------
         if (!WONLY) {
@@ -379,7 +459,7 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
                 const uint32_t i = base + lane;
                 uint32_t hs = 0, pos = 0, fval = 0; bool have = false, search = false;
                 if (i < ns) {
-                    const uint2 r = S.srec[i];
+                    const uint2 r = S.wrec[TILE_Q - 1 - i];
                     hs = r.x & 0xFFFFu; pos = r.y & 0xFFFu;
                     fval = r.y >> 16; have = (r.y & S_TOUCHED) != 0;             // pre-tile value
                     const uint32_t slot = S.side[hs & (SIDE_N - 1)];
@@ -448,7 +528,6 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
         uint32_t tch = (v != 0 || bit_test(S.vbit, i)) ? 0x10000u : 0u;
         final_tab[(size_t)run * 65536 + i] = v | tch;
     }
-    if (tid == 0 && S.overflow) atomicOr(&st->nonquiet, 2u);  // suspect list overflow: fall back to the in-order kernel
 }
 
 // carry-in fold for decode: initial dictionary is all zero values (chameleon.rs:41): nothing touched.
@@ -468,12 +547,13 @@ __global__ void dec_carry_scan(const uint32_t* __restrict__ final_tab, uint32_t 
 __global__ void dec_tail(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, uint32_t* __restrict__ dict,
                          DecStatus* __restrict__ st, uint64_t* __restrict__ d_out_size) {
     if (threadIdx.x || blockIdx.x) return;
-    if (st->nonquiet) return;                 // the caller's in-order fallback produces the result
+    if (st->nonquiet) { if (d_out_size) *d_out_size = 0; return; }   // gave up: the caller's in-order fallback (queued behind) produces the result
     if (st->error) { st->out_bytes = 0; if (d_out_size) *d_out_size = 0; return; }
     uint64_t idx = st->tail_off, oidx = st->main_blocks * 256;
     Protection ps; ps.init();
     ps.counter = st->main_blocks;             // quiet so far: penalty 0, start 1 (protection_state.rs:9-16,38-43)
     ps.previous_incompressible = st->last_main_inc;
+    if (st->seq) { ps.copy_penalty = st->ps_penalty; ps.copy_penalty_start = st->ps_start; ps.previous_incompressible = st->ps_prev; }
     bool bad = false, overflow = false;
     auto emit = [&](uint32_t q) {
         if (oidx + 4 > cap) { overflow = true; return; }
@@ -592,6 +672,7 @@ cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     dec_block_offsets<<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off); ++*launches;
     const uint64_t maxblocks = nbytes / 136 + 2;
     dec_quiet_check<<<(unsigned)((maxblocks + 255) / 256), 256, 0, stream>>>(d_in, blk_off, st, cap); ++*launches;
+    dec_seq_walk<<<1, SW_THREADS, 0, stream>>>(d_in, nbytes, cap, blk_off, st); ++*launches;   // only runs for streams with copy-mode blocks
     // run count from an upper bound of the block count (the kernel reads the real one from the status block)
     uint64_t tiles_ub = (maxblocks + 63) / 64;
     uint32_t nruns = (uint32_t)(tiles_ub / 16); if (nruns < 1) nruns = 1; if (nruns > (uint32_t)num_sms) nruns = num_sms;

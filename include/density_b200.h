@@ -88,6 +88,10 @@ DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_i
    blocks), 1 = parallel decoder only (size 0 if it had to give up), 3 = in-order kernel only. */
 DENSITY_B200_API int density_b200_decode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                     uint64_t* d_out_size, void* stream, int path);
+/* Diagnostic: status of the last parallel Chameleon decode on the current device (synchronises the device):
+   out10 = {out_bytes, main_blocks, tail_off, nonquiet, error, last_main_inc, in_order_boundaries, penalty, penalty_start, prev_incompressible}.
+   in_order_boundaries != 0: the stream had copy-mode blocks (codec.rs:89-92) and the boundaries came from the in-order walk. */
+DENSITY_B200_API int density_b200_decode_status(uint64_t* out10);
 /* Same contract for decode; `cap` must be >= the original length. */
 DENSITY_B200_API int density_b200_decode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                uint64_t* d_out_size, void* stream);

@@ -193,6 +193,36 @@ def test_chameleon_full_size_1gib_text_bit_exact(torch_cuda, codecs):
     assert int(d_sz.item()) == m and torch.equal(d_out[:m], d_out2[:m])
 
 
+def test_chameleon_beyond_4gib_prefix_and_round_trip(torch_cuda, codecs):
+    """5 GiB of text in one call (byte offsets past 2^32, the per-GPU shard scale of SURVEY.md §8d config 5). Size-independent checks:
+    the stream of a prefix is a prefix of the stream (codec.rs:72-80 walks the blocks in order; a 64 MiB prefix is compared with the
+    oracle), the stream decodes back to the input on the device, and the output size obeys codec.rs:18-21."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    C = codecs["chameleon"]
+    n = 5 * (1 << 30) + 256 * 3 + 1
+    if torch.cuda.mem_get_info()[0] < 24 * (1 << 30):
+        pytest.skip("needs 24 GiB of free device memory")
+    d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for off in range(0, n, 1 << 30):                       # page-aligned pieces of the same counter-based text
+        k = min(1 << 30, n - off)
+        d_in[off:off + k] = synth.synth_text(k, device="cuda", first_page=off // synth.PAGE)
+    d_out = torch.empty(C.safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("chameleon", d_in, d_out, d_sz)
+    torch.cuda.synchronize()
+    m = int(d_sz.item())
+    assert 0 < m <= C.safe_encode_buffer_size(n)
+    npre = 64 << 20
+    want = oracle.encode("chameleon", d_in[:npre].cpu().numpy())
+    assert (d_out[:want.size].cpu().numpy() == want).all()
+    d_dec = torch.empty(n, dtype=torch.uint8, device="cuda")
+    density_b200.decode_device("chameleon", d_out, m, d_dec, d_sz)
+    torch.cuda.synchronize()
+    assert int(d_sz.item()) == n and torch.equal(d_dec, d_in)
+
+
 @pytest.mark.parametrize("alg", ALGS)
 def test_device_pointers_through_reference_symbols(torch_cuda, codecs, alg):
     torch = torch_cuda
@@ -303,13 +333,34 @@ def test_chameleon_decode_paths_on_text(torch_cuda, codecs, path, nbytes):
     assert (d_out[:nbytes].cpu().numpy() == data).all()
 
 
-@pytest.mark.parametrize("kind", ["random", "mixed", "low", "zeros"])
-def test_chameleon_decode_copy_mode_streams_fall_back_exactly(codecs, kind):
-    C = codecs["chameleon"]
-    data = payload(kind, 3 * (1 << 20) + 5, seed=5)
-    enc = oracle.encode("chameleon", data)
-    dec = gpu_decode(C, enc, data.size)
-    assert dec.size == data.size and (dec == data).all()
+@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("kind,nbytes", [("random", 3 * (1 << 20) + 5), ("mixed", 3 * (1 << 20) + 5), ("low", 3 * (1 << 20) + 5), ("zeros", 3 * (1 << 20) + 5),
+                                         ("random", 70001), ("mixed", 280004), ("random", 256 * 40 + 263), ("random", 256 * 40 + 264),
+                                         ("smixed", 40 * (1 << 20) + 3)])
+def test_chameleon_decode_copy_mode_streams(torch_cuda, codecs, path, kind, nbytes):
+    """Streams with copy-mode blocks (codec.rs:89-92): the candidate boundary walks are void, `dec_seq_walk` redoes the boundaries in
+    order with the exact automaton and the parallel dictionary passes run on its block list. path 1 = parallel decoder only (no
+    in-order fallback), so this is the parallel path being checked; the streams come from the oracle."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    data = synth.synth_mixed(nbytes).numpy() if kind == "smixed" else payload(kind, nbytes, seed=5)
+    enc, copied = oracle.encode("chameleon", data, return_copied=True)
+    if kind in ("random", "mixed", "smixed"):
+        assert copied > 0
+    d_enc = torch.from_numpy(enc.copy()).cuda()
+    d_out = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.decode_device("chameleon", d_enc, enc.size, d_out, d_sz, path=path)
+    torch.cuda.synchronize()
+    if path == 1 and int(d_sz.item()) == 0 and kind in ("low", "zeros"):
+        pytest.skip("pathological tile (thousands of readers of one freshly written bucket): path 0 falls back to the in-order kernel")
+    assert int(d_sz.item()) == nbytes
+    assert (d_out[:nbytes].cpu().numpy() == data).all()
+    # host-pointer entry point (the reference symbol) on the same stream
+    if nbytes <= 3 * (1 << 20) + 5:
+        dec = gpu_decode(codecs["chameleon"], enc, data.size)
+        assert dec.size == data.size and (dec == data).all()
 
 
 def test_chameleon_decode_adversarial_same_bucket(torch_cuda, codecs):

@@ -5,7 +5,7 @@ from density_b200 import synth, codec
 n = next((int(a) for a in sys.argv[1:] if a.isdigit()), 256) << 20
 ALG = next((a for a in sys.argv[1:] if a in ("cheetah", "lion")), "cheetah")
 C = density_b200.CODECS[ALG]
-d_in = synth.synth_text(n, device="cuda")
+d_in = synth.synth_mixed(n, device="cuda") if "--mixed" in sys.argv else synth.synth_text(n, device="cuda")
 d_out = torch.empty(C.safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
 d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
 for _ in range(2): codec.encode_device(ALG, d_in, d_out, d_sz, path=1)

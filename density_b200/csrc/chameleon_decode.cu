@@ -52,7 +52,9 @@ __device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return *reinterpre
 
 // ---- 1a. candidate walks -----------------------------------------------------------------------------------------------
 // res[chunk][cand] = exit_idx | nblocks << 8 | term_rel << 16   (exit_idx == TERM: walk ended inside this chunk at relative
-// offset term_rel because fewer than 264 bytes remain: that is where codec.rs's tail loop takes over)
+// offset term_rel because fewer than 264 bytes remain: that is where codec.rs's tail loop takes over).
+// exit_idx != TERM: bits 16-18 = {two consecutive incompressible blocks inside, first block incompressible, last block incompressible}
+// for dec_seq_walk, which may jump over a chunk only if the protection automaton provably stays in its encoded mode there.
 __global__ void __launch_bounds__(160) dec_chunk_walk(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, uint32_t* __restrict__ res) {
     __shared__ __align__(16) uint8_t s[CH + 288];
     const uint32_t c = blockIdx.x;
@@ -65,15 +67,20 @@ __global__ void __launch_bounds__(160) dec_chunk_walk(const uint8_t* __restrict_
     const uint32_t cand = threadIdx.x;
     if (cand >= NCAND) return;
     uint32_t off = cand * 2, nb = 0, exitc = TERM, term = 0;
+    uint32_t pair = 0, first = 0, prev = 0;
     while (true) {
         if (off >= (uint32_t)CH) { exitc = (off - CH) >> 1; break; }
         if (base + off + 264 > n) { term = off; break; }
         const uint16_t* p = reinterpret_cast<const uint16_t*>(s + off);
         const uint32_t hits = __popc((uint32_t)p[0] | ((uint32_t)p[1] << 16)) + __popc((uint32_t)p[2] | ((uint32_t)p[3] << 16));
+        const uint32_t inc = hits <= 4 ? 1u : 0u;           // consumed >= 256 (codec.rs:98)
+        if (nb == 0) first = inc;
+        pair |= inc & prev;
+        prev = inc;
         off += 264 - 2 * hits;
         ++nb;
     }
-    res[(size_t)c * NCAND + cand] = exitc | (nb << 8) | (term << 16);
+    res[(size_t)c * NCAND + cand] = exitc | (nb << 8) | ((exitc == TERM ? term : (pair | (first << 1) | (prev << 2))) << 16);
     (void)nchunks;
 }
 
@@ -131,7 +138,8 @@ __global__ void dec_chunk_entries(const uint32_t* __restrict__ res, uint32_t nch
 
 // ---- 1e. one offset per block ------------------------------------------------------------------------------------------------
 __global__ void dec_block_offsets(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, const uint32_t* __restrict__ c_entry,
-                                  const uint64_t* __restrict__ c_blockbase, uint64_t* __restrict__ blk_off) {
+                                  const uint64_t* __restrict__ c_blockbase, uint64_t* __restrict__ blk_off, const DecStatus* __restrict__ only_if_seq) {
+    if (only_if_seq && !only_if_seq->seq) return;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const uint32_t e = c_entry[c];
@@ -165,12 +173,17 @@ __global__ void dec_quiet_check(const uint8_t* __restrict__ in, const uint64_t* 
 }
 
 // ---- 2b. in-order boundary walk for streams with copy-mode blocks (codec.rs:88-100 with protection_state.rs) ---------------------
-// The stream is cut into fixed 16 KiB windows; window k (plus the bytes a block starting at its end can reach) is staged in shared
-// memory by the loader warps while thread 0 still walks window k-1, so the walk never waits for DRAM: ~50 cycles per block.
-constexpr int SW_WIN = 16384;
-constexpr int SW_LOAD = SW_WIN + 16;         // + the 8 signature bytes of a block starting at the window's last byte, rounded up to 16
-constexpr int SW_THREADS = 160;              // warp 0 walks, warps 1-4 load
-constexpr int SW_PER = (SW_LOAD / 16 + 127) / 128;   // 16-byte pieces per loader thread
+// One CTA; thread 0 carries (stream offset, block count, protection state) through the stream chunk by chunk.
+//  * A chunk is JUMPED in O(1) from dec_chunk_walk's table when the automaton provably stays in encoded mode inside it (penalty 0
+//    on entry, no two consecutive incompressible blocks inside, none across the entry seam): all its blocks are encoded blocks, the
+//    table row gives the exit offset and block count, and dec_block_offsets fills in the per-block offsets afterwards in parallel.
+//  * Any other chunk is WALKED block by block from a shared-memory copy (the whole CTA stages its 16 KiB), marking copy-mode blocks.
+// Table rows are staged 32 chunks at a time, so a jumped chunk costs ~50 cycles, a walked block ~100: a stream with a handful of
+// copy-mode episodes costs little more than the quiet path, one that is mostly incompressible ~2 GB/s of stream.
+constexpr int SW_LOAD = CH + 16;             // + the 8 signature bytes of a block starting at the chunk's last byte, rounded up to 16
+constexpr int SW_THREADS = 256;
+constexpr int SW_BATCH = 32;                 // table rows staged at a time
+enum : uint32_t { SW_ROWS = 0, SW_DIRTY = 1, SW_DONE = 2 };
 __device__ __forceinline__ uint4 sw_load16(const uint8_t* __restrict__ in, uint64_t g, uint64_t n, bool al16) {
     uint4 v = make_uint4(0, 0, 0, 0);
     if (al16 && g + 16 <= n) return *reinterpret_cast<const uint4*>(in + g);
@@ -178,49 +191,77 @@ __device__ __forceinline__ uint4 sw_load16(const uint8_t* __restrict__ in, uint6
     for (int k = 0; k < 16; ++k) if (g + k < n) vb[k] = in[g + k];
     return v;
 }
-__global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __restrict__ in, uint64_t n, uint64_t cap, uint64_t* __restrict__ blk_off,
+__global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __restrict__ in, uint64_t n, uint64_t cap, uint32_t nchunks,
+                                                           const uint32_t* __restrict__ res, uint32_t* __restrict__ c_entry,
+                                                           uint64_t* __restrict__ c_blockbase, uint64_t* __restrict__ blk_off,
                                                            DecStatus* __restrict__ st) {
     if (!(st->nonquiet & 1u)) return;
-    __shared__ __align__(16) uint8_t win[2][SW_LOAD];
+    __shared__ __align__(16) uint8_t win[SW_LOAD];
+    __shared__ uint32_t rows[SW_BATCH * NCAND];
+    __shared__ uint32_t s_cmd, s_chunk;
     const uint32_t tid = threadIdx.x;
     const bool al16 = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
-    const uint64_t nwin = (n + SW_WIN - 1) / SW_WIN;
     Protection ps; ps.init();
-    uint64_t idx = 0, b = 0;
-    // prologue: window 0
-    if (tid >= 32)
-        for (uint32_t i = (tid - 32) * 16; i < (uint32_t)SW_LOAD; i += 128 * 16) *reinterpret_cast<uint4*>(win[0] + i) = sw_load16(in, i, n, al16);
-    __syncthreads();
-    for (uint64_t k = 0; k < nwin; ++k) {
-        const uint64_t wbase = k * SW_WIN;
-        if (tid >= 32) {                                   // loaders: window k+1 into the other buffer (all loads in flight before the stores)
-            uint4 v[SW_PER];
-            const uint64_t nb = wbase + SW_WIN;
-#pragma unroll
-            for (int t = 0; t < SW_PER; ++t) {
-                const uint32_t i = ((tid - 32) + t * 128) * 16;
-                v[t] = (k + 1 < nwin && i < (uint32_t)SW_LOAD) ? sw_load16(in, nb + i, n, al16) : make_uint4(0, 0, 0, 0);
+    uint64_t idx = 0, b = 0;        // meaningful in thread 0 only
+    uint32_t cb = 0, cb_valid = 0;  // staged rows: chunks [cb, cb + cb_valid)
+    while (true) {
+        if (tid == 0) {
+            uint32_t cmd = SW_DONE, c = 0;
+            while (n - idx >= 264) {
+                c = (uint32_t)(idx / CH);
+                if (c < cb || c >= cb + cb_valid) { cmd = SW_ROWS; break; }
+                const uint32_t e = (uint32_t)(idx - (uint64_t)c * CH) >> 1;          // < NCAND: a block is at most 264 bytes
+                const uint32_t r = rows[(c - cb) * NCAND + e];
+                const uint32_t ex = r & 0xFFu, fl = r >> 16;
+                if (ps.copy_penalty == 0 && ex != TERM && !(fl & 1u) && !(ps.previous_incompressible && (fl & 2u))) {
+                    const uint32_t nb = (r >> 8) & 0xFFu;
+                    c_entry[c] = e; c_blockbase[c] = b;
+                    // protection_state.rs:18-24 over nb blocks that never enter copy mode: the penalty start halves on every 16th block
+                    const uint64_t k = (ps.counter + nb + 15) / 16 - (ps.counter + 15) / 16;
+                    if (ps.copy_penalty_start > 1) { const uint32_t sh = k > 8 ? 8u : (uint32_t)k; const uint32_t v = ps.copy_penalty_start >> sh; ps.copy_penalty_start = v ? v : 1u; }
+                    ps.counter += nb;
+                    ps.previous_incompressible = (fl >> 2) & 1u;
+                    b += nb;
+                    idx = (uint64_t)(c + 1) * CH + 2 * ex;
+                } else { cmd = SW_DIRTY; break; }
             }
-#pragma unroll
-            for (int t = 0; t < SW_PER; ++t) {
-                const uint32_t i = ((tid - 32) + t * 128) * 16;
-                if (i < (uint32_t)SW_LOAD) *reinterpret_cast<uint4*>(win[(k + 1) & 1] + i) = v[t];
-            }
-        } else if (tid == 0) {                             // walker: every block that STARTS inside window k
-            const uint8_t* w = win[k & 1];
-            const uint64_t wend = wbase + SW_WIN;
-            while (idx < wend && n - idx >= 264) {
-                if (ps.revert_to_copy()) {                                  // codec.rs:89-92
-                    blk_off[b++] = idx | BLK_COPY; idx += 256; ps.decay();
-                } else {
-                    const uint8_t* p = w + (idx - wbase);
-                    const uint32_t hits = __popc(ldu16(p) | (ldu16(p + 2) << 16)) + __popc(ldu16(p + 4) | (ldu16(p + 6) << 16));
-                    const uint32_t consumed = 264 - 2 * hits;
-                    blk_off[b++] = idx; idx += consumed; ps.update(consumed >= 256);   // codec.rs:94-98
+            s_cmd = cmd; s_chunk = c;
+        }
+        __syncthreads();
+        const uint32_t cmd = s_cmd, c = s_chunk;
+        if (cmd == SW_DONE) break;
+        if (cmd == SW_ROWS) {
+            cb = c; cb_valid = (nchunks - c < (uint32_t)SW_BATCH) ? nchunks - c : (uint32_t)SW_BATCH;
+            for (uint32_t i = tid; i < cb_valid * NCAND; i += SW_THREADS) rows[i] = res[(size_t)cb * NCAND + i];
+        } else {
+            const uint64_t wbase = (uint64_t)c * CH;
+            for (uint32_t i = tid * 16; i < (uint32_t)SW_LOAD; i += SW_THREADS * 16) *reinterpret_cast<uint4*>(win + i) = sw_load16(in, wbase + i, n, al16);
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(win);
+                const uint64_t wend = wbase + CH;
+                c_entry[c] = TERM;                                           // dec_block_offsets leaves this chunk alone
+                while (idx < wend && n - idx >= 264) {
+                    if (ps.revert_to_copy()) {                               // codec.rs:89-92
+                        blk_off[b++] = idx | BLK_COPY; idx += 256; ps.decay();
+                    } else {
+                        const uint32_t o = (uint32_t)(idx - wbase), sh = (o & 2u) * 8;
+                        const uint32_t w0 = w32[o >> 2], w1 = w32[(o >> 2) + 1], w2 = w32[(o >> 2) + 2];
+                        const uint32_t hits = __popc(__funnelshift_r(w0, w1, sh)) + __popc(__funnelshift_r(w1, w2, sh));
+                        const uint32_t consumed = 264 - 2 * hits;
+                        blk_off[b++] = idx; idx += consumed; ps.update(consumed >= 256);   // codec.rs:94-98
+                    }
                 }
             }
         }
         __syncthreads();
+    }
+    // the chunk in which the main loop ended (if it was not walked it has no block either) and everything behind it carry no blocks
+    {
+        __shared__ uint32_t s_first_free;
+        if (tid == 0) s_first_free = (uint32_t)(idx / CH);
+        __syncthreads();
+        for (uint32_t c = s_first_free + tid; c < nchunks; c += SW_THREADS) c_entry[c] = TERM;
     }
     if (tid == 0) {
         st->main_blocks = b; st->tail_off = idx;
@@ -669,10 +710,12 @@ cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     dec_group_compose<<<ngroups, 160, 0, stream>>>(res, nchunks, gres); ++*launches;
     dec_top_walk<<<1, 32, 0, stream>>>(gres, ngroups, nbytes, g_entry, g_bb, st); ++*launches;
     dec_chunk_entries<<<(ngroups + 127) / 128, 128, 0, stream>>>(res, nchunks, g_entry, g_bb, ngroups, c_entry, c_bb); ++*launches;
-    dec_block_offsets<<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off); ++*launches;
+    dec_block_offsets<<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off, nullptr); ++*launches;
     const uint64_t maxblocks = nbytes / 136 + 2;
     dec_quiet_check<<<(unsigned)((maxblocks + 255) / 256), 256, 0, stream>>>(d_in, blk_off, st, cap); ++*launches;
-    dec_seq_walk<<<1, SW_THREADS, 0, stream>>>(d_in, nbytes, cap, blk_off, st); ++*launches;   // only runs for streams with copy-mode blocks
+    // streams with copy-mode blocks only (both kernels return at once otherwise): in-order walk, then the offsets of the jumped chunks
+    dec_seq_walk<<<1, SW_THREADS, 0, stream>>>(d_in, nbytes, cap, nchunks, res, c_entry, c_bb, blk_off, st); ++*launches;
+    dec_block_offsets<<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off, st); ++*launches;
     // run count from an upper bound of the block count (the kernel reads the real one from the status block)
     uint64_t tiles_ub = (maxblocks + 63) / 64;
     uint32_t nruns = (uint32_t)(tiles_ub / 16); if (nruns < 1) nruns = 1; if (nruns > (uint32_t)num_sms) nruns = num_sms;

@@ -336,7 +336,7 @@ def test_chameleon_decode_paths_on_text(torch_cuda, codecs, path, nbytes):
 @pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("kind,nbytes", [("random", 3 * (1 << 20) + 5), ("mixed", 3 * (1 << 20) + 5), ("low", 3 * (1 << 20) + 5), ("zeros", 3 * (1 << 20) + 5),
                                          ("random", 70001), ("mixed", 280004), ("random", 256 * 40 + 263), ("random", 256 * 40 + 264),
-                                         ("smixed", 40 * (1 << 20) + 3)])
+                                         ("smixed", 40 * (1 << 20) + 3), ("bursts", 24 * (1 << 20) + 777)])
 def test_chameleon_decode_copy_mode_streams(torch_cuda, codecs, path, kind, nbytes):
     """Streams with copy-mode blocks (codec.rs:89-92): the candidate boundary walks are void, `dec_seq_walk` redoes the boundaries in
     order with the exact automaton and the parallel dictionary passes run on its block list. path 1 = parallel decoder only (no
@@ -344,9 +344,14 @@ def test_chameleon_decode_copy_mode_streams(torch_cuda, codecs, path, kind, nbyt
     torch = torch_cuda
     import density_b200
     from density_b200 import synth
-    data = synth.synth_mixed(nbytes).numpy() if kind == "smixed" else payload(kind, nbytes, seed=5)
+    if kind == "bursts":      # text with a few incompressible bursts: most chunks are jumped over, the ones around the bursts are walked
+        data = synth.synth_text(nbytes).numpy().copy()
+        for off, ln in ((1 << 20, 65536), (5 * (1 << 20) + 300, 1500), (17 * (1 << 20) + 2, 300000), (nbytes - 3000, 3000)):
+            data[off:off + ln] = synth.random_bytes(ln, 99).numpy()
+    else:
+        data = synth.synth_mixed(nbytes).numpy() if kind == "smixed" else payload(kind, nbytes, seed=5)
     enc, copied = oracle.encode("chameleon", data, return_copied=True)
-    if kind in ("random", "mixed", "smixed"):
+    if kind in ("random", "mixed", "smixed", "bursts"):
         assert copied > 0
     d_enc = torch.from_numpy(enc.copy()).cuda()
     d_out = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")

@@ -15,9 +15,10 @@
 //  2. Protection.  `dec_quiet_check`: if no two consecutive blocks are incompressible (>= 256 bytes consumed, codec.rs:98)
 //     the automaton never leaves its initial state and no block is in copy mode (same argument as the encoder). Otherwise
 //     the candidate walks are void (a copy-mode block has no signature) and `dec_seq_walk` redoes the boundaries in order
-//     with the exact automaton: one warp streams the signatures through shared-memory windows (a block costs ~50 cycles
-//     instead of a dependent DRAM access) and marks the copy-mode blocks; the dictionary passes below then run unchanged
-//     (a copy-mode block is 64 raw quads that neither read nor write the dictionary, codec.rs:89-92).
+//     with the exact automaton: chunks in which the automaton provably stays in encoded mode are jumped in O(1) from the
+//     candidate table, the others are walked block by block from shared memory and their copy-mode blocks marked; the
+//     dictionary passes below then run unchanged (a copy-mode block is 64 raw quads that neither read nor write the
+//     dictionary, codec.rs:89-92).
 //  3. Dictionary.  `cham_decode_pass`: one persistent CTA per contiguous run of blocks, the run's dictionary in shared
 //     memory as 16-bit fingerprints (common.cuh). Per tile of 4096 quads: PLAIN quads (~8 %) are the writers, MAP quads the
 //     readers; barrier-phased optimistic protocol — A readers read / B writers publish / C readers re-read; unchanged means
@@ -42,7 +43,7 @@ struct DecStatus {
     unsigned long long out_bytes;
     unsigned long long main_blocks;      // blocks decoded by the parallel main loop (codec.rs:88-100)
     unsigned long long tail_off;         // stream offset where the tail loop starts
-    unsigned int nonquiet, error;        // nonquiet bit 0: copy-mode blocks present (cleared again by dec_seq_walk); bit 1: pathological tile
+    unsigned int nonquiet, error;        // nonquiet bit 0: copy-mode blocks present (cleared again by dec_seq_walk)
     unsigned int last_main_inc, seq;     // seq: the boundaries come from dec_seq_walk, automaton state below is valid
     unsigned int ps_penalty, ps_start, ps_prev, pad;   // protection state after the main loop (protection_state.rs:9-16)
 };

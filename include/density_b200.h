@@ -84,8 +84,9 @@ DENSITY_B200_API int density_b200_encode_device(int alg, const uint8_t* d_in, si
    not settle), 1 = run-parallel encoder only (*d_out_size == 0 if the copy map did not settle), 3 = in-order kernel. */
 DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                     uint64_t* d_out_size, void* stream, int path);
-/* Decode counterpart: path 0 = auto (parallel Chameleon decoder, exact in-order kernel when the stream has copy-mode
-   blocks), 1 = parallel decoder only (size 0 if it had to give up), 3 = in-order kernel only. */
+/* Decode counterpart: path 0 = auto (parallel Chameleon decoder, also for streams with copy-mode blocks; the exact in-order
+   kernel is queued behind it as a safety net and for Cheetah / Lion), 1 = parallel decoder only (size 0 if it had to give
+   up), 3 = in-order kernel only. */
 DENSITY_B200_API int density_b200_decode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                     uint64_t* d_out_size, void* stream, int path);
 /* Diagnostic: status of the last parallel Chameleon decode on the current device (synchronises the device):

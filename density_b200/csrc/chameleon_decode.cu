@@ -86,18 +86,29 @@ __global__ void __launch_bounds__(160) dec_chunk_walk(const uint8_t* __restrict_
 }
 
 // ---- 1b. compose the maps of GROUP consecutive chunks ----------------------------------------------------------------------
-// gres[g][cand] = {exit_idx (or TERM), blocks, term_chunk, term_rel}
+// gres[g][cand] = {exit_idx (or TERM), blocks, term_chunk, term_rel}; exit_idx != TERM: z = the chunk flags composed along the path
+// (bit 0: two consecutive incompressible blocks anywhere inside the group, bit 1: first block, bit 2: last block incompressible,
+//  bit 3: short last group, which dec_seq_walk never jumps)
 __global__ void dec_group_compose(const uint32_t* __restrict__ res, uint32_t nchunks, uint4* __restrict__ gres) {
     const uint32_t g = blockIdx.x, cand = threadIdx.x;
     if (cand >= NCAND) return;
     uint32_t idx = cand, blocks = 0, tchunk = 0, trel = 0;
+    uint32_t pair = 0, first = 0, last = 0, have = 0;
     const uint32_t c0 = g * GROUP, c1 = min(nchunks, c0 + GROUP);
     for (uint32_t c = c0; c < c1; ++c) {
         const uint32_t r = res[(size_t)c * NCAND + idx];
-        blocks += (r >> 8) & 0xFFu;
+        const uint32_t nb = (r >> 8) & 0xFFu;
+        blocks += nb;
         idx = r & 0xFFu;
         if (idx == TERM) { tchunk = c; trel = r >> 16; break; }
+        if (nb) {
+            const uint32_t fl = r >> 16;
+            if (!have) { first = (fl >> 1) & 1u; have = 1; } else pair |= last & (fl >> 1) & 1u;
+            pair |= fl & 1u;
+            last = (fl >> 2) & 1u;
+        }
     }
+    if (idx != TERM) tchunk = pair | (first << 1) | (last << 2) | ((c1 - c0 < (uint32_t)GROUP) ? 8u : 0u);
     gres[(size_t)g * NCAND + cand] = make_uint4(idx, blocks, tchunk, trel);
 }
 
@@ -121,12 +132,15 @@ __global__ void dec_top_walk(const uint4* __restrict__ gres, uint32_t ngroups, u
 }
 
 // ---- 1d. per chunk: true entry + block index -----------------------------------------------------------------------------
+constexpr uint32_t G_SKIP = 0xFEu;     // g_entry: dec_seq_walk handled this group chunk by chunk (c_entry already written)
 __global__ void dec_chunk_entries(const uint32_t* __restrict__ res, uint32_t nchunks, const uint32_t* __restrict__ g_entry,
                                   const uint64_t* __restrict__ g_blockbase, uint32_t ngroups, uint32_t* __restrict__ c_entry,
-                                  uint64_t* __restrict__ c_blockbase) {
+                                  uint64_t* __restrict__ c_blockbase, const DecStatus* __restrict__ only_if_seq) {
+    if (only_if_seq && !only_if_seq->seq) return;
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ngroups) return;
     uint32_t idx = g_entry[g]; uint64_t blocks = g_blockbase[g];
+    if (idx == G_SKIP) return;
     const uint32_t c0 = g * GROUP, c1 = min(nchunks, c0 + GROUP);
     for (uint32_t c = c0; c < c1; ++c) {
         c_entry[c] = idx; c_blockbase[c] = blocks;
@@ -192,10 +206,18 @@ __device__ __forceinline__ uint4 sw_load16(const uint8_t* __restrict__ in, uint6
     for (int k = 0; k < 16; ++k) if (g + k < n) vb[k] = in[g + k];
     return v;
 }
+// Jump over nb blocks that never enter copy mode (protection_state.rs:18-24,37-47): the penalty start halves on every 16th block.
+__device__ __forceinline__ void sw_jump(Protection& ps, uint32_t nb, uint32_t last_inc) {
+    const uint64_t k = (ps.counter + nb + 15) / 16 - (ps.counter + 15) / 16;
+    if (ps.copy_penalty_start > 1) { const uint32_t sh = k > 8 ? 8u : (uint32_t)k; const uint32_t v = ps.copy_penalty_start >> sh; ps.copy_penalty_start = v ? v : 1u; }
+    ps.counter += nb;
+    ps.previous_incompressible = last_inc;
+}
 __global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __restrict__ in, uint64_t n, uint64_t cap, uint32_t nchunks,
-                                                           const uint32_t* __restrict__ res, uint32_t* __restrict__ c_entry,
-                                                           uint64_t* __restrict__ c_blockbase, uint64_t* __restrict__ blk_off,
-                                                           DecStatus* __restrict__ st) {
+                                                           const uint32_t* __restrict__ res, const uint4* __restrict__ gres, uint32_t ngroups,
+                                                           uint32_t* __restrict__ g_entry, uint64_t* __restrict__ g_blockbase,
+                                                           uint32_t* __restrict__ c_entry, uint64_t* __restrict__ c_blockbase,
+                                                           uint64_t* __restrict__ blk_off, DecStatus* __restrict__ st) {
     if (!(st->nonquiet & 1u)) return;
     __shared__ __align__(16) uint8_t win[SW_LOAD];
     __shared__ uint32_t rows[SW_BATCH * NCAND];
@@ -204,24 +226,34 @@ __global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __rest
     const bool al16 = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
     Protection ps; ps.init();
     uint64_t idx = 0, b = 0;        // meaningful in thread 0 only
+    uint32_t g_next = 0;            // first group not entered yet (thread 0)
     uint32_t cb = 0, cb_valid = 0;  // staged rows: chunks [cb, cb + cb_valid)
     while (true) {
         if (tid == 0) {
             uint32_t cmd = SW_DONE, c = 0;
             while (n - idx >= 264) {
                 c = (uint32_t)(idx / CH);
-                if (c < cb || c >= cb + cb_valid) { cmd = SW_ROWS; break; }
                 const uint32_t e = (uint32_t)(idx - (uint64_t)c * CH) >> 1;          // < NCAND: a block is at most 264 bytes
+                if (c / GROUP == g_next) {
+                    // entering a group of 64 chunks: jump over all of it if the automaton provably stays in encoded mode inside
+                    const uint32_t g = g_next++;
+                    const uint4 gr = gres[(size_t)g * NCAND + e];
+                    if (ps.copy_penalty == 0 && gr.x != TERM && !(gr.z & 9u) && !(ps.previous_incompressible && (gr.z & 2u))) {
+                        g_entry[g] = e; g_blockbase[g] = b;
+                        sw_jump(ps, gr.y, (gr.z >> 2) & 1u);
+                        b += gr.y;
+                        idx = (uint64_t)(g + 1) * GROUP * CH + 2 * gr.x;
+                        continue;
+                    }
+                    g_entry[g] = G_SKIP;                                             // chunk by chunk below
+                }
+                if (c < cb || c >= cb + cb_valid) { cmd = SW_ROWS; break; }
                 const uint32_t r = rows[(c - cb) * NCAND + e];
                 const uint32_t ex = r & 0xFFu, fl = r >> 16;
                 if (ps.copy_penalty == 0 && ex != TERM && !(fl & 1u) && !(ps.previous_incompressible && (fl & 2u))) {
                     const uint32_t nb = (r >> 8) & 0xFFu;
                     c_entry[c] = e; c_blockbase[c] = b;
-                    // protection_state.rs:18-24 over nb blocks that never enter copy mode: the penalty start halves on every 16th block
-                    const uint64_t k = (ps.counter + nb + 15) / 16 - (ps.counter + 15) / 16;
-                    if (ps.copy_penalty_start > 1) { const uint32_t sh = k > 8 ? 8u : (uint32_t)k; const uint32_t v = ps.copy_penalty_start >> sh; ps.copy_penalty_start = v ? v : 1u; }
-                    ps.counter += nb;
-                    ps.previous_incompressible = (fl >> 2) & 1u;
+                    sw_jump(ps, nb, (fl >> 2) & 1u);
                     b += nb;
                     idx = (uint64_t)(c + 1) * CH + 2 * ex;
                 } else { cmd = SW_DIRTY; break; }
@@ -259,10 +291,11 @@ __global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __rest
     }
     // the chunk in which the main loop ended (if it was not walked it has no block either) and everything behind it carry no blocks
     {
-        __shared__ uint32_t s_first_free;
-        if (tid == 0) s_first_free = (uint32_t)(idx / CH);
+        __shared__ uint32_t s_first_free, s_gnext;
+        if (tid == 0) { s_first_free = (uint32_t)(idx / CH); s_gnext = g_next; }
         __syncthreads();
         for (uint32_t c = s_first_free + tid; c < nchunks; c += SW_THREADS) c_entry[c] = TERM;
+        for (uint32_t g = s_gnext + tid; g < ngroups; g += SW_THREADS) g_entry[g] = G_SKIP;
     }
     if (tid == 0) {
         st->main_blocks = b; st->tail_off = idx;
@@ -710,12 +743,14 @@ cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     dec_chunk_walk<<<nchunks, 160, 0, stream>>>(d_in, nbytes, nchunks, res); ++*launches;
     dec_group_compose<<<ngroups, 160, 0, stream>>>(res, nchunks, gres); ++*launches;
     dec_top_walk<<<1, 32, 0, stream>>>(gres, ngroups, nbytes, g_entry, g_bb, st); ++*launches;
-    dec_chunk_entries<<<(ngroups + 127) / 128, 128, 0, stream>>>(res, nchunks, g_entry, g_bb, ngroups, c_entry, c_bb); ++*launches;
+    dec_chunk_entries<<<(ngroups + 127) / 128, 128, 0, stream>>>(res, nchunks, g_entry, g_bb, ngroups, c_entry, c_bb, nullptr); ++*launches;
     dec_block_offsets<<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off, nullptr); ++*launches;
     const uint64_t maxblocks = nbytes / 136 + 2;
     dec_quiet_check<<<(unsigned)((maxblocks + 255) / 256), 256, 0, stream>>>(d_in, blk_off, st, cap); ++*launches;
-    // streams with copy-mode blocks only (both kernels return at once otherwise): in-order walk, then the offsets of the jumped chunks
-    dec_seq_walk<<<1, SW_THREADS, 0, stream>>>(d_in, nbytes, cap, nchunks, res, c_entry, c_bb, blk_off, st); ++*launches;
+    // streams with copy-mode blocks only (the three kernels return at once otherwise): in-order walk, then the entries of the chunks of
+    // jumped groups and the offsets of the blocks of jumped chunks
+    dec_seq_walk<<<1, SW_THREADS, 0, stream>>>(d_in, nbytes, cap, nchunks, res, gres, ngroups, g_entry, g_bb, c_entry, c_bb, blk_off, st); ++*launches;
+    dec_chunk_entries<<<(ngroups + 127) / 128, 128, 0, stream>>>(res, nchunks, g_entry, g_bb, ngroups, c_entry, c_bb, st); ++*launches;
     dec_block_offsets<<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off, st); ++*launches;
     // run count from an upper bound of the block count (the kernel reads the real one from the status block)
     uint64_t tiles_ub = (maxblocks + 63) / 64;

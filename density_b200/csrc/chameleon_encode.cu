@@ -39,7 +39,6 @@ namespace cham {
 // Pass 1: flag pass
 // ------------------------------------------------------------------------------------------------------
 constexpr int FP_THREADS = 1024;
-constexpr int FP_WARPS = FP_THREADS / 32;
 constexpr int FP_QPT = 4;                          // quads per thread per tile
 constexpr int TILE_Q = FP_THREADS * FP_QPT;        // 4096 quads = 16 KiB = 64 blocks
 constexpr int SIDE_N = 8192;                       // first-misser table (u32), indexed by hash & (SIDE_N-1)

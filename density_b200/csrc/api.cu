@@ -111,6 +111,8 @@ static bool is_device_pointer(const void* p) {
 }
 
 // path: 0 auto (fast path with exact fallback), 1 fast only (no fallback), 2 protected walk only, 3 scalar kernel
+// path 4 (internal): Chameleon auto path for callers that may block on the stream (the synchronous reference-facing entry points): the
+// copy-map iteration gets up to 12 more batches of 8 rounds before the in-order walk may take over
 static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                 uint64_t* d_out_size, cudaStream_t stream, int path) {
     uint64_t launches = 0;
@@ -132,7 +134,9 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
                 for (int i = 0; i < 4; ++i) if (!ev[i]) cudaEventCreate(&ev[i]);
             }
             e = cham_encode_phase1(d_in, n, c->ws.p, L, nruns, nullptr, stream, &launches, ev);
-            if (e == cudaSuccess)
+            if (e == cudaSuccess && path == 4)
+                e = cham_encode_phase2_blocking(d_in, n, c->ws.p, L, nruns, d_out, cap, d_out_size, 12, stream, &launches);
+            else if (e == cudaSuccess)
                 e = cham_encode_phase2(d_in, n, c->ws.p, L, nruns, nullptr, d_out, cap, d_out_size, path == 0, false, stream, &launches, ev);
             if (ev != nullptr && e == cudaSuccess) c->prof_count++;
         }
@@ -302,7 +306,7 @@ static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_
         if (e != cudaSuccess) { set_error("staging cudaMalloc", e); return 0; }
         d_out = c->stage_out.p;
     }
-    int rc = encode ? encode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream, 0)
+    int rc = encode ? encode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream, alg == ALG_CHAMELEON ? 4 : 0)
                     : decode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream);
     if (rc != DENSITY_B200_OK) { cudaStreamSynchronize(c->stream); return 0; }
     e = cudaMemcpyAsync(c->h_size, c->d_size, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
@@ -375,7 +379,7 @@ int density_b200_decode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* 
 }
 int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
                                     void* stream, int path) {
-    if (path < 0 || path > 3) { set_error("bad path"); return DENSITY_B200_EARG; }
+    if (path < 0 || path > 4 || (path == 4 && alg != ALG_CHAMELEON)) { set_error("bad path"); return DENSITY_B200_EARG; }
     return device_entry(true, alg, d_in, n, d_out, cap, d_out_size, stream, path);
 }
 int density_b200_decode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
@@ -506,6 +510,17 @@ int density_b200_last_encode_was_fast(void) {
     Status st;
     if (cudaMemcpy(&st, c->ws.p + c->layout.status, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return st.nonquiet ? 0 : 1;
+}
+
+/* diagnostic: status block of the last Chameleon encode on the current device (synchronises) */
+int density_b200_encode_status(uint64_t* out6) {
+    DeviceCtx* c = current_ctx();
+    if (!c || !c->ws.p) return DENSITY_B200_EARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    Status st;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&st, c->ws.p + c->layout.status, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return DENSITY_B200_ECUDA;
+    out6[0] = st.out_bytes; out6[1] = st.nonquiet; out6[2] = st.error; out6[3] = st.first_nonquiet_block; out6[4] = st.converged; out6[5] = st.iter_changed;
+    return DENSITY_B200_OK;
 }
 
 void density_b200_shutdown(void) {

@@ -974,78 +974,139 @@ cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
 }
 
 // Phase 2: carry-in tables, resolve, sizes, scan, (protected fallback), emit.
-cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
-                               const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
-                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches,
-                               cudaEvent_t* ev) {
+// Phase 2 in three parts, so that a caller that may synchronise with the host (the reference-facing entry points do anyway) can run
+// further rounds of the copy-map iteration instead of dropping to the in-order walk when PROT_ITERS rounds were not enough
+// (chains of copy-mode episodes that feed each other through the dictionary, e.g. the same incompressible blob several times).
+//   begin : carry-in tables, first-touch flags, block sizes + quiet check
+//   rounds: fixed-point rounds it_first .. it_last of the copy map (every kernel exits at once unless the quiet check failed and the
+//           map has not settled yet); prot_iterate owns 8 grid-barrier slots, so a batch is at most 8 rounds and `reset_barriers`
+//           clears them first
+//   finish: the exact in-order walk if the map still has not settled (optional), sizes under the copy map, scan, emit
+cudaError_t cham_phase2_begin(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns, const uint32_t* d_carry_in,
+                              bool assume_prev_inc, cudaStream_t stream, uint64_t* launches) {
+    (void)d_in;
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
+    Status* st = reinterpret_cast<Status*>(ws + L.status);
+    uint32_t* sigw = reinterpret_cast<uint32_t*>(ws + L.sigw);
+    cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
+                                                    reinterpret_cast<uint32_t*>(ws + L.carry), nullptr);
+    cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+                                                     reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw);
+    cham_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(sigw, nullptr, nbytes, nblocks, ntiles, 0, 1, assume_prev_inc ? 1 : 0, st,
+                                                          reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t cham_phase2_rounds(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns, const uint32_t* d_carry_in,
+                               int it_first, int it_last, bool reset_barriers, cudaStream_t stream, uint64_t* launches) {
+    const uint64_t nblocks = (nbytes + 255) / 256;
+    const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
+    Status* st = reinterpret_cast<Status*>(ws + L.status);
+    uint32_t* sigw = reinterpret_cast<uint32_t*>(ws + L.sigw);
+    uint8_t* copymap = ws + L.copymap;
+    uint8_t* copymap2 = ws + L.copymap2;
+    uint32_t* seg_state = reinterpret_cast<uint32_t*>(ws + L.seg_state);
+    uint8_t* incb = ws + L.incb;
+    int num_ctas = 0;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_ctas, cudaDevAttrMultiProcessorCount, dev); if (num_ctas < 1) num_ctas = 1; }
+    const uint32_t nseg = (uint32_t)((nblocks + PSEG - 1) / PSEG);
+    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(d_in);
+    const uint64_t nquads = nbytes / 4;
+    if (it_last - it_first >= 8) return cudaErrorInvalidValue;
+    if (reset_barriers) {
+        cudaError_t e = cudaMemsetAsync(st->barrier, 0, sizeof(st->barrier), stream);
+        if (e != cudaSuccess) return e;
+    }
+    for (int it = it_first; it <= it_last; ++it) {
+        if (it > 0) {   // flags under the current copy map (copy-mode blocks hidden from the dictionary)
+            cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(in32, nquads, ntiles, nruns, sigw,
+                reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+                reinterpret_cast<uint32_t*>(ws + L.final_tab), copymap, st);
+            cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
+                                                            reinterpret_cast<uint32_t*>(ws + L.carry), nullptr, st);
+            cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+                                                             reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw, st);
+            *launches += 3;
+        }
+        prot_iterate<<<num_ctas, PI_THREADS, 0, stream>>>(sigw, nbytes, nblocks, nseg, st, it, incb, copymap, copymap2,
+                                                          seg_state, seg_state + (nseg + 1));
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t cham_phase2_finish(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out, size_t cap,
+                               uint64_t* d_out_size, bool with_copy_map, cudaStream_t stream, uint64_t* launches, cudaEvent_t* ev) {
     const uint64_t nblocks = (nbytes + 255) / 256;
     const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
     const uint32_t ngroups = (ntiles + SCAN_G - 1) / SCAN_G;
     Status* st = reinterpret_cast<Status*>(ws + L.status);
     uint32_t* sigw = reinterpret_cast<uint32_t*>(ws + L.sigw);
     uint8_t* copymap = ws + L.copymap;
-    if (nblocks == 0) {
-        return cudaMemsetAsync(d_out_size, 0, sizeof(uint64_t), stream);
-    }
-    cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
-                                                    reinterpret_cast<uint32_t*>(ws + L.carry), nullptr);
-    ++*launches;
-    cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
-                                                     reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw);
-    ++*launches;
-    const uint32_t ts_blocks = (ntiles + 7) / 8;
-    cham_tile_sizes<<<ts_blocks, 256, 0, stream>>>(sigw, nullptr, nbytes, nblocks, ntiles, 0, 1, assume_prev_inc ? 1 : 0, st,
-                                                   reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
-    ++*launches;
-    if (allow_protected_fallback) {
-        // Everything below exits immediately unless the quiet check failed (status->nonquiet).
-        // 1) parallel fixed-point iteration of the copy map; 2) if it does not converge in PROT_ITERS rounds, the exact
-        //    in-order walk; 3) the sizes again, now with the copy map.
-        uint8_t* copymap2 = ws + L.copymap2;
-        uint32_t* seg_state = reinterpret_cast<uint32_t*>(ws + L.seg_state);
-        uint8_t* incb = ws + L.incb;
-        int num_ctas = 0;
-        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_ctas, cudaDevAttrMultiProcessorCount, dev); if (num_ctas < 1) num_ctas = 1; }
-        const uint32_t nseg = (uint32_t)((nblocks + PSEG - 1) / PSEG);
-        const uint32_t* in32 = reinterpret_cast<const uint32_t*>(d_in);
-        const uint64_t nquads = nbytes / 4;
-        constexpr int PROT_ITERS = 4;
-        for (int it = 0; it <= PROT_ITERS; ++it) {
-            if (it > 0) {   // flags under the current copy map (copy-mode blocks hidden from the dictionary)
-                cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(in32, nquads, ntiles, nruns, sigw,
-                    reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
-                    reinterpret_cast<uint32_t*>(ws + L.final_tab), copymap, st);
-                cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
-                                                                reinterpret_cast<uint32_t*>(ws + L.carry), nullptr, st);
-                cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
-                                                                 reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw, st);
-                *launches += 3;
-            }
-            prot_iterate<<<num_ctas, PI_THREADS, 0, stream>>>(sigw, nbytes, nblocks, nseg, st, it, incb, copymap, copymap2,
-                                                              seg_state, seg_state + (nseg + 1));
-            ++*launches;
-        }
-        cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(in32, nbytes, st, 1, sigw, copymap);
-        ++*launches;
-        cham_tile_sizes<<<ts_blocks, 256, 0, stream>>>(sigw, copymap, nbytes, nblocks, ntiles, 1, 0, 0, st,
-                                                       reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
-        ++*launches;
+    if (with_copy_map) {
+        // the exact in-order walk if the iteration did not settle; then the sizes again, now with the copy map
+        cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, st, 1, sigw, copymap);
+        cham_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(sigw, copymap, nbytes, nblocks, ntiles, 1, 0, 0, st,
+                                                              reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
+        *launches += 2;
     }
     scan_groups_local<<<ngroups, SCAN_T, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.tile_bytes), ntiles,
                                                       reinterpret_cast<uint32_t*>(ws + L.tile_local),
                                                       reinterpret_cast<uint64_t*>(ws + L.group_total));
-    ++*launches;
     scan_group_totals<<<1, SCAN_T, 0, stream>>>(reinterpret_cast<uint64_t*>(ws + L.group_total), ngroups,
                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), st, (uint64_t)cap, d_out_size);
-    ++*launches;
+    *launches += 2;
     if (ev) cudaEventRecord(ev[2], stream);
     cham_emit<<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw,
-                                                 allow_protected_fallback ? copymap : nullptr, 1, st,
+                                                 with_copy_map ? copymap : nullptr, 1, st,
                                                  reinterpret_cast<uint32_t*>(ws + L.tile_local),
                                                  reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
     ++*launches;
     if (ev) cudaEventRecord(ev[3], stream);
     return cudaGetLastError();
+}
+
+// host-visible verdict of the iteration so far (synchronises the stream): 0 quiet or settled, 1 more rounds needed
+cudaError_t cham_phase2_needs_more(uint8_t* ws, const ChamLayout& L, cudaStream_t stream, bool* more) {
+    Status h;
+    cudaError_t e = cudaMemcpyAsync(&h, ws + L.status, sizeof h, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    *more = h.nonquiet && !h.converged && !h.error;
+    return cudaSuccess;
+}
+
+constexpr int PROT_ITERS = 4;   // rounds 0..4 are always enqueued (they cost ~3 us each when the input is quiet)
+
+cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns,
+                               const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                               bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches,
+                               cudaEvent_t* ev) {
+    if (nbytes == 0) return cudaMemsetAsync(d_out_size, 0, sizeof(uint64_t), stream);
+    cudaError_t e = cham_phase2_begin(d_in, nbytes, ws, L, nruns, d_carry_in, assume_prev_inc, stream, launches);
+    if (e == cudaSuccess && allow_protected_fallback)
+        e = cham_phase2_rounds(d_in, nbytes, ws, L, nruns, d_carry_in, 0, PROT_ITERS, false, stream, launches);
+    if (e == cudaSuccess) e = cham_phase2_finish(d_in, nbytes, ws, L, d_out, cap, d_out_size, allow_protected_fallback, stream, launches, ev);
+    return e;
+}
+
+// Same result, for callers that may block: after the standard rounds the host looks at the verdict and keeps iterating in batches of 8
+// rounds (up to `max_batches`) before the in-order walk is allowed to take over.
+cudaError_t cham_encode_phase2_blocking(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns, uint8_t* d_out,
+                                        size_t cap, uint64_t* d_out_size, int max_batches, cudaStream_t stream, uint64_t* launches) {
+    if (nbytes == 0) return cudaMemsetAsync(d_out_size, 0, sizeof(uint64_t), stream);
+    cudaError_t e = cham_phase2_begin(d_in, nbytes, ws, L, nruns, nullptr, false, stream, launches);
+    if (e == cudaSuccess) e = cham_phase2_rounds(d_in, nbytes, ws, L, nruns, nullptr, 0, PROT_ITERS, false, stream, launches);
+    for (int batch = 0; e == cudaSuccess && batch < max_batches; ++batch) {
+        bool more = false;
+        e = cham_phase2_needs_more(ws, L, stream, &more);
+        if (e != cudaSuccess || !more) break;
+        e = cham_phase2_rounds(d_in, nbytes, ws, L, nruns, nullptr, 8, 15, true, stream, launches);
+    }
+    if (e == cudaSuccess) e = cham_phase2_finish(d_in, nbytes, ws, L, d_out, cap, d_out_size, true, stream, launches, nullptr);
+    return e;
 }
 
 cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches) {

@@ -19,6 +19,8 @@ cudaError_t cham_encode_phase2(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
                                const uint32_t* d_carry_in, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
                                bool allow_protected_fallback, bool assume_prev_inc, cudaStream_t stream, uint64_t* launches,
                                cudaEvent_t* ev = nullptr);
+cudaError_t cham_encode_phase2_blocking(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns, uint8_t* d_out,
+                                        size_t cap, uint64_t* d_out_size, int max_batches, cudaStream_t stream, uint64_t* launches);
 cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out,
                                        size_t cap, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
 

@@ -79,7 +79,10 @@ DENSITY_B200_API int density_b200_encode_device(int alg, const uint8_t* d_in, si
 /* Test/diagnostic variant: choose the encode path explicitly.
    Chameleon: path 0 = auto (run-parallel fast path, exact protection-aware fallback when needed),
    1 = fast path only (no fallback; out size is only valid if the stream is "quiet"),
-   2 = exact in-order protection-aware walk only, 3 = in-order single-thread kernel.
+   2 = exact in-order protection-aware walk only, 3 = in-order single-thread kernel,
+   4 = like 0, but the call may BLOCK on the stream: if the copy map has not settled after the 5 rounds that are always enqueued,
+   the host keeps iterating (up to 96 more rounds) before the in-order walk takes over; this is what the nine reference
+   symbols use (they are synchronous anyway).
    Cheetah / Lion: 0 = auto (run-parallel encoder; the in-order kernel, queued behind it, runs only if the copy map did
    not settle), 1 = run-parallel encoder only (*d_out_size == 0 if the copy map did not settle), 3 = in-order kernel. */
 DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
@@ -89,6 +92,9 @@ DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_i
    up), 3 = in-order kernel only. */
 DENSITY_B200_API int density_b200_decode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                     uint64_t* d_out_size, void* stream, int path);
+/* Diagnostic: status of the last Chameleon encode on the current device (synchronises the device):
+   out6 = {out_bytes, nonquiet (copy mode was needed), error, first_nonquiet_block, copy map converged, scratch}. */
+DENSITY_B200_API int density_b200_encode_status(uint64_t* out6);
 /* Diagnostic: status of the last parallel Chameleon decode on the current device (synchronises the device):
    out10 = {out_bytes, main_blocks, tail_off, nonquiet, error, last_main_inc, in_order_boundaries, penalty, penalty_start, prev_incompressible}.
    in_order_boundaries != 0: the stream had copy-mode blocks (codec.rs:89-92) and the boundaries came from the in-order walk. */

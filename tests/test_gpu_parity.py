@@ -223,6 +223,37 @@ def test_chameleon_beyond_4gib_prefix_and_round_trip(torch_cuda, codecs):
     assert int(d_sz.item()) == n and torch.equal(d_dec, d_in)
 
 
+def test_chameleon_encode_chained_copy_mode_episodes(torch_cuda, codecs):
+    """The same incompressible blob 14 times in 64 MiB of text: episode k sees what episode k-1 left in the dictionary (the text never
+    touches those buckets), so the copy map settles one episode per fixed-point round. The reference-facing entry point keeps
+    iterating from the host instead of dropping to the in-order walk; the result is the oracle's stream either way."""
+    torch = torch_cuda
+    import ctypes
+    import density_b200
+    from density_b200 import synth
+    n = 64 * (1 << 20) + 100
+    data = synth.synth_text(n).numpy().copy()
+    blob = synth.random_bytes(65536, 99).numpy()
+    for k in range(14):
+        off = (2 + 4 * k) * (1 << 20) + 256 * k
+        data[off:off + blob.size] = blob
+    want, copied = oracle.encode("chameleon", data, return_copied=True)
+    assert copied > 0
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    m = codecs["chameleon"].encode(d_in, d_out)            # chameleon_encode(): device pointers, synchronous
+    assert m == want.size and (d_out[:m].cpu().numpy() == want).all()
+    st = (ctypes.c_uint64 * 6)()
+    assert density_b200.load().density_b200_encode_status(st) == 0
+    assert st[1] == 1 and st[4] == 1, "copy map should have settled by iteration, not by the in-order walk"
+    # the stream-ordered auto path (fixed round budget, in-order walk as the fallback) gives the same bytes
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_out.zero_()
+    density_b200.encode_device("chameleon", d_in, d_out, d_sz, path=0)
+    torch.cuda.synchronize()
+    assert int(d_sz.item()) == want.size and (d_out[:want.size].cpu().numpy() == want).all()
+
+
 @pytest.mark.parametrize("alg", ALGS)
 def test_device_pointers_through_reference_symbols(torch_cuda, codecs, alg):
     torch = torch_cuda

@@ -197,7 +197,7 @@ __global__ void dec_quiet_check(const uint8_t* __restrict__ in, const uint64_t* 
 // copy-mode episodes costs little more than the quiet path, one that is mostly incompressible ~2 GB/s of stream.
 constexpr int SW_LOAD = CH + 16;             // + the 8 signature bytes of a block starting at the chunk's last byte, rounded up to 16
 constexpr int SW_THREADS = 256;
-constexpr int SW_BATCH = 32;                 // table rows staged at a time
+constexpr int SW_BATCH = 24;                 // table rows staged at a time
 enum : uint32_t { SW_ROWS = 0, SW_DIRTY = 1, SW_DONE = 2 };
 __device__ __forceinline__ uint4 sw_load16(const uint8_t* __restrict__ in, uint64_t g, uint64_t n, bool al16) {
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __rest
                                                            uint32_t* __restrict__ c_entry, uint64_t* __restrict__ c_blockbase,
                                                            uint64_t* __restrict__ blk_off, DecStatus* __restrict__ st) {
     if (!(st->nonquiet & 1u)) return;
-    __shared__ __align__(16) uint8_t win[SW_LOAD];
+    __shared__ __align__(16) uint8_t win[2][SW_LOAD];   // the chunk being walked + the next one, prefetched during the walk
     __shared__ uint32_t rows[SW_BATCH * NCAND];
     __shared__ uint32_t s_cmd, s_chunk;
     const uint32_t tid = threadIdx.x;
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __rest
     uint64_t idx = 0, b = 0;        // meaningful in thread 0 only
     uint32_t g_next = 0;            // first group not entered yet (thread 0)
     uint32_t cb = 0, cb_valid = 0;  // staged rows: chunks [cb, cb + cb_valid)
+    uint32_t wchunk0 = 0xFFFFFFFFu, wchunk1 = 0xFFFFFFFFu;   // which chunk each window buffer holds (uniform over the CTA)
     while (true) {
         if (tid == 0) {
             uint32_t cmd = SW_DONE, c = 0;
@@ -268,10 +269,29 @@ __global__ void __launch_bounds__(SW_THREADS) dec_seq_walk(const uint8_t* __rest
             for (uint32_t i = tid; i < cb_valid * NCAND; i += SW_THREADS) rows[i] = res[(size_t)cb * NCAND + i];
         } else {
             const uint64_t wbase = (uint64_t)c * CH;
-            for (uint32_t i = tid * 16; i < (uint32_t)SW_LOAD; i += SW_THREADS * 16) *reinterpret_cast<uint4*>(win + i) = sw_load16(in, wbase + i, n, al16);
-            __syncthreads();
+            int cur = (wchunk0 == c) ? 0 : (wchunk1 == c) ? 1 : -1;
+            if (cur < 0) {                                                   // not prefetched: the whole CTA stages it now
+                cur = 0; wchunk0 = c;
+                for (uint32_t i = tid * 16; i < (uint32_t)SW_LOAD; i += SW_THREADS * 16) *reinterpret_cast<uint4*>(win[0] + i) = sw_load16(in, wbase + i, n, al16);
+                __syncthreads();
+            }
+            if (tid >= 32 && c + 1 < nchunks) {                              // the others fetch the next chunk while thread 0 walks this one
+                constexpr int PER = (SW_LOAD / 16 + (SW_THREADS - 32) - 1) / (SW_THREADS - 32);
+                uint4 v[PER];
+#pragma unroll
+                for (int t = 0; t < PER; ++t) {
+                    const uint32_t i = ((tid - 32) + t * (SW_THREADS - 32)) * 16;
+                    v[t] = (i < (uint32_t)SW_LOAD) ? sw_load16(in, wbase + CH + i, n, al16) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int t = 0; t < PER; ++t) {
+                    const uint32_t i = ((tid - 32) + t * (SW_THREADS - 32)) * 16;
+                    if (i < (uint32_t)SW_LOAD) *reinterpret_cast<uint4*>(win[cur ^ 1] + i) = v[t];
+                }
+            }
+            if (c + 1 < nchunks) { if (cur) wchunk0 = c + 1; else wchunk1 = c + 1; }
             if (tid == 0) {
-                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(win);
+                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(win[cur]);
                 const uint64_t wend = wbase + CH;
                 c_entry[c] = TERM;                                           // dec_block_offsets leaves this chunk alone
                 while (idx < wend && n - idx >= 264) {

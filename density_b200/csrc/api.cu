@@ -155,11 +155,21 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
             if (e != cudaSuccess) { set_error("cudaMemsetAsync", e); return DENSITY_B200_ECUDA; }
             c->chee_epoch = 0;
         }
-        const uint32_t epoch_base = c->chee_epoch + 1;
-        c->chee_epoch += 32;
         uint32_t* d_conv = reinterpret_cast<uint32_t*>(c->ws.p + pw);
         uint8_t* const tabs[3] = {tb[0].p, tb[1].p, tb[2].p};
-        e = chee_encode_parallel(alg, d_in, n, d_out, cap, c->ws.p, tabs, epoch_base, c->num_sms, d_out_size, d_conv, stream, &launches);
+        // path 4 (callers that may block): read the verdict and resume the iteration up to 12 times before the in-order kernel takes over
+        for (int attempt = 0; attempt <= (path == 4 ? 12 : 0); ++attempt) {
+            if (attempt > 0) {
+                uint32_t conv = 0;
+                e = cudaMemcpyAsync(&conv, d_conv, sizeof conv, cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+                if (e != cudaSuccess || conv) break;
+            }
+            const uint32_t epoch_base = c->chee_epoch + 1;
+            c->chee_epoch += 32;
+            e = chee_encode_parallel(alg, d_in, n, d_out, cap, c->ws.p, tabs, epoch_base, c->num_sms, d_out_size, d_conv, attempt > 0, stream, &launches);
+            if (e != cudaSuccess) break;
+        }
         if (e == cudaSuccess && path != 1)
             e = scalar_encode(alg, d_in, n, d_out, cap, c->ws.p + pw + 256, d_out_size, stream, &launches, d_conv);
         c->last_was_chameleon_fastpath_capable = 0;
@@ -306,7 +316,7 @@ static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_
         if (e != cudaSuccess) { set_error("staging cudaMalloc", e); return 0; }
         d_out = c->stage_out.p;
     }
-    int rc = encode ? encode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream, alg == ALG_CHAMELEON ? 4 : 0)
+    int rc = encode ? encode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream, 4)
                     : decode_device_locked(c, alg, d_in, n, d_out, d_cap, c->d_size, c->stream);
     if (rc != DENSITY_B200_OK) { cudaStreamSynchronize(c->stream); return 0; }
     e = cudaMemcpyAsync(c->h_size, c->d_size, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
@@ -379,7 +389,7 @@ int density_b200_decode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* 
 }
 int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
                                     void* stream, int path) {
-    if (path < 0 || path > 4 || (path == 4 && alg != ALG_CHAMELEON)) { set_error("bad path"); return DENSITY_B200_EARG; }
+    if (path < 0 || path > 4) { set_error("bad path"); return DENSITY_B200_EARG; }
     return device_entry(true, alg, d_in, n, d_out, cap, d_out_size, stream, path);
 }
 int density_b200_decode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,

@@ -688,9 +688,11 @@ size_t chee_tables_bytes(int alg, int region, size_t nbytes, int num_sms) {
 // Enqueue the parallel Cheetah / Lion encode. *d_converged (device u32) != 0 afterwards means d_out / d_out_size hold the result;
 // otherwise the caller's in-order kernel (queued behind, gated on that flag) produces it. `epoch_base`: the caller hands out 32 fresh
 // epochs (values in 1 .. 2^28) per call and clears `tables` if it ever has to reuse one.
+// `resume`: continue an iteration that a previous call on the same input and workspace left unsettled (callers that may block read
+// *d_converged and call again): the stages on the prefix are skipped and the whole-input stages start from the last committed map.
 cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, uint8_t* const tables[3],
-                                 uint32_t epoch_base, int num_sms, uint64_t* d_out_size, uint32_t* d_converged, cudaStream_t stream,
-                                 uint64_t* launches) {
+                                 uint32_t epoch_base, int num_sms, uint64_t* d_out_size, uint32_t* d_converged, bool resume,
+                                 cudaStream_t stream, uint64_t* launches) {
     const bool lion = alg == ALG_LION;
     const uint32_t bbytes = lion ? 64 : 128;
     const uint32_t nruns = chee_pick_runs(nbytes, num_sms);
@@ -739,9 +741,12 @@ cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, ui
     };
 
     // A stage = up to 8 rounds on one Status block (prot_iterate owns 8 grid-barrier slots per block).
+    // test hook: DENSITY_B200_CHEE_ROUNDS=k (1..7) cuts every stage to rounds first..k so that the resume path can be exercised
+    int last_it = 7;
+    if (const char* v = getenv("DENSITY_B200_CHEE_ROUNDS")) { const int k = atoi(v); if (k >= 1 && k <= 7) last_it = k; }
     auto stage = [&](Status* st, const Status* inherit, int first_it, size_t nb, uint32_t runs, uint32_t ep0) -> cudaError_t {
         chee_chain_gate<<<1, 1, 0, stream>>>(st, inherit); ++*launches;
-        for (int it = first_it; it <= 7; ++it) {
+        for (int it = first_it; it <= last_it; ++it) {
             cudaError_t err = round(st, it, nb, runs, ep0 + (uint32_t)it);
             if (err != cudaSuccess) return err;
         }
@@ -754,15 +759,17 @@ cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, ui
         // prefix does not depend on what follows). Stages B1, B2 then start from that map and normally confirm it in one round
         // over the whole input.
         const size_t nbA = (size_t)PREFIX_TILES * TILE_B * 128;
-        e = cudaMemsetAsync(cm, 0, (size_t)ntiles * TILE_B * 2, stream);
-        if (e != cudaSuccess) return e;
-        e = stage(&stages[0], nullptr, 0, nbA, PREFIX_TILES, epoch_base);
-        if (e == cudaSuccess) e = stage(&stages[1], &stages[0], 1, nbA, PREFIX_TILES, epoch_base + 8);
+        if (!resume) {
+            e = cudaMemsetAsync(cm, 0, (size_t)ntiles * TILE_B * 2, stream);
+            if (e != cudaSuccess) return e;
+            e = stage(&stages[0], nullptr, 0, nbA, PREFIX_TILES, epoch_base);
+            if (e == cudaSuccess) e = stage(&stages[1], &stages[0], 1, nbA, PREFIX_TILES, epoch_base + 8);
+        }
         if (e == cudaSuccess) e = stage(&stages[2], nullptr, 1, nbytes, nruns, epoch_base + 16);
         if (e == cudaSuccess) e = stage(&stages[3], &stages[2], 1, nbytes, nruns, epoch_base + 24);
         st = &stages[3];
     } else {
-        e = stage(&stages[0], nullptr, 0, nbytes, nruns, epoch_base);
+        e = stage(&stages[0], nullptr, resume ? 1 : 0, nbytes, nruns, epoch_base);
         if (e == cudaSuccess) e = stage(&stages[1], &stages[0], 1, nbytes, nruns, epoch_base + 8);
         st = &stages[1];
     }

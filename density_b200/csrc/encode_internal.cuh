@@ -36,8 +36,8 @@ cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint3
 size_t chee_workspace_bytes(size_t nbytes, int num_sms);
 size_t chee_tables_bytes(int alg, int region, size_t nbytes, int num_sms);
 cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, uint8_t* const tables[3],
-                                 uint32_t epoch_base, int num_sms, uint64_t* d_out_size, uint32_t* d_converged, cudaStream_t stream,
-                                 uint64_t* launches);
+                                 uint32_t epoch_base, int num_sms, uint64_t* d_out_size, uint32_t* d_converged, bool resume,
+                                 cudaStream_t stream, uint64_t* launches);
 
 // chameleon_decode.cu
 size_t cham_decode_workspace_bytes(size_t nbytes, int nruns_max);

@@ -84,7 +84,8 @@ DENSITY_B200_API int density_b200_encode_device(int alg, const uint8_t* d_in, si
    the host keeps iterating (up to 96 more rounds) before the in-order walk takes over; this is what the nine reference
    symbols use (they are synchronous anyway).
    Cheetah / Lion: 0 = auto (run-parallel encoder; the in-order kernel, queued behind it, runs only if the copy map did
-   not settle), 1 = run-parallel encoder only (*d_out_size == 0 if the copy map did not settle), 3 = in-order kernel. */
+   not settle), 1 = run-parallel encoder only (*d_out_size == 0 if the copy map did not settle), 3 = in-order kernel,
+   4 = like 0 but may BLOCK: the host reads the verdict and resumes the iteration (up to 12 times) before the in-order kernel. */
 DENSITY_B200_API int density_b200_encode_device_path(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                     uint64_t* d_out_size, void* stream, int path);
 /* Decode counterpart: path 0 = auto (parallel Chameleon decoder, also for streams with copy-mode blocks; the exact in-order

@@ -254,6 +254,35 @@ def test_chameleon_encode_chained_copy_mode_episodes(torch_cuda, codecs):
     assert int(d_sz.item()) == want.size and (d_out[:want.size].cpu().numpy() == want).all()
 
 
+@pytest.mark.parametrize("alg", ["cheetah", "lion"])
+@pytest.mark.parametrize("nbytes", [33 * (1 << 20) + 66, (1 << 20) + 5])
+def test_cheetah_lion_blocking_iteration_resumes(torch_cuda, codecs, alg, nbytes, monkeypatch):
+    """Path 4 (what the synchronous reference symbols use): when the copy map has not settled after the enqueued stages the host reads
+    the verdict and resumes the iteration instead of leaving the stream to the in-order kernel. The test hook cuts every stage to one
+    round so that the resume path is exercised on ordinary text; the in-order kernel would need seconds for the larger input."""
+    import time
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    data = synth.synth_text(nbytes).numpy()
+    want = oracle.encode(alg, data)
+    d_in = torch.from_numpy(data.copy()).cuda()
+    d_out = torch.zeros(codecs[alg].safe_encode_buffer_size(nbytes) + 64, dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device(alg, d_in, d_out, d_sz, path=4)          # warm (workspace allocation)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("DENSITY_B200_CHEE_ROUNDS", "1")
+    d_out.zero_(); d_sz.zero_()
+    t0 = time.perf_counter()
+    density_b200.encode_device(alg, d_in, d_out, d_sz, path=4)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n = int(d_sz.item())
+    assert n == want.size and (d_out[:n].cpu().numpy() == want).all()
+    if nbytes > (1 << 25):
+        assert dt < 1.0, f"{dt:.2f} s: the in-order kernel produced this, not the resumed iteration"
+
+
 @pytest.mark.parametrize("alg", ALGS)
 def test_device_pointers_through_reference_symbols(torch_cuda, codecs, alg):
     torch = torch_cuda

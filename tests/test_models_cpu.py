@@ -94,3 +94,29 @@ def test_decode_walk_jump_equals_the_stepwise_automaton():
         j = _Protection(0, start, prev, counter)
         _sw_jump(j, nb, bool(inc[-1]))
         assert (a.penalty, a.start, a.prev, a.counter) == (0, j.start, j.prev, j.counter)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_decode_boundary_walk_model_equals_in_order_parse(seed):
+    """dec_chunk_walk / dec_group_compose / dec_seq_walk (chunk and group jumps) / dec_chunk_entries / dec_block_offsets, modelled in
+    tools/proto_decode_walk.py with small chunks, against the plain in-order parse of oracle streams with copy-mode episodes."""
+    from tools import proto_decode_walk as W
+    rng = np.random.default_rng(100 + seed)
+    d = np.fromfile(os.path.join(ROOT, "tests", "golden", "dickens_200k.bin"), np.uint8)
+    parts = []
+    pos = int(rng.integers(0, 50000))
+    for _ in range(int(rng.integers(2, 7))):
+        ln = int(rng.integers(2000, 40000)); parts.append(d[pos:pos + ln]); pos = (pos + ln) % 150000
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            parts.append(rng.integers(0, 256, int(rng.integers(300, 20000)), dtype=np.uint8))       # incompressible burst
+        elif kind == 1:
+            parts.append(np.arange(int(rng.integers(100, 3000)), dtype=np.uint32).view(np.uint8))    # all-plain counters
+        elif kind == 2:
+            parts.append(np.zeros(int(rng.integers(100, 5000)), np.uint8))
+    data = np.concatenate(parts)
+    enc, copied = oracle.encode("chameleon", data, return_copied=True)
+    want = W.reference_parse(enc)
+    assert sum(1 for o in want[0] if o & W.COPY) > 0 or copied == 0
+    got = W.model_parse(enc, CH=2048, GROUP=4)
+    assert got == want

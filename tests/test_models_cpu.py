@@ -120,3 +120,14 @@ def test_decode_boundary_walk_model_equals_in_order_parse(seed):
     assert sum(1 for o in want[0] if o & W.COPY) > 0 or copied == 0
     got = W.model_parse(enc, CH=2048, GROUP=4)
     assert got == want
+
+
+@pytest.mark.parametrize("name", ["kat", "dickens", "low"])
+def test_planned_cheetah_decoder_model_round_trips(name):
+    """tools/proto_cheetah_decode_full.py (the decomposition the next round's Cheetah decoder is built on: chunk-map values run-parallel,
+    predicted values by iteration on the contexts, copy-mode blocks and tail in order) reproduces the input from the oracle's stream."""
+    from tools import proto_cheetah_decode_full as D
+    data = _cases()[name]
+    enc = oracle.encode("cheetah", data)
+    got, rounds, ncopy, produced = D.decode(enc, data.size, nruns=3)
+    assert produced == data.size and (got == data).all()

@@ -131,3 +131,13 @@ def test_planned_cheetah_decoder_model_round_trips(name):
     enc = oracle.encode("cheetah", data)
     got, rounds, ncopy, produced = D.decode(enc, data.size, nruns=3)
     assert produced == data.size and (got == data).all()
+
+
+@pytest.mark.parametrize("name", ["kat", "dickens", "mixed"])
+def test_planned_lion_decoder_model_round_trips(name):
+    """tools/proto_lion_decode_full.py: 6-byte signatures, 3-bit flags, 5 hashes per context in the serial hash chain, values per context."""
+    from tools import proto_lion_decode_full as D
+    data = _cases()[name]
+    enc = oracle.encode("lion", data)
+    got, ncopy, produced = D.decode(enc, data.size, nruns=3)
+    assert produced == data.size and (got == data).all()

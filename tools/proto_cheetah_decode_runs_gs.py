@@ -19,7 +19,24 @@ M = 0x9D6EF916
 UNK = None
 
 
-def iterate(q, nruns, max_rounds=200):
+def chase(start, steps, table):
+    """x -> hash(table[x]) for `steps` links on a STATIC table (nothing writes inside a stretch of predicted quads): stop early at a
+    fixed point or cycle and jump the rest."""
+    x = start; seen = {}; k = 0
+    while k < steps:
+        if x in seen:                                   # cycle of length p: skip whole periods
+            p = k - seen[x]
+            k += ((steps - k) // p) * p
+            seen = {}
+            if k >= steps:
+                break
+        seen[x] = k
+        x = ((table.get(x, 0) * M) & 0xFFFFFFFF) >> 16
+        k += 1
+    return x
+
+
+def iterate(q, nruns, max_rounds=200, sweep=False):
     flags, h = true_flags(q)
     ql = q.tolist(); n = len(ql)
     bounds = [n * r // nruns for r in range(nruns)] + [n]
@@ -56,6 +73,12 @@ def iterate(q, nruns, max_rounds=200):
         for r in range(nruns):
             new_snap.append(dict(acc)); new_carry.append(c)
             acc.update(finals[r][0]); c = finals[r][1]
+        if sweep:
+            # carry the context through runs that consist of predicted quads only (flags are known): their tables are static, so the last
+            # hash of run r is a chase of (run length) links from its first context on the snapshot run r starts from
+            for r in range(1, nruns):
+                if new_carry[r] is UNK and new_carry[r - 1] is not UNK and all(f == 3 for f in flags[bounds[r - 1]:bounds[r]]):
+                    new_carry[r] = chase(new_carry[r - 1], bounds[r] - bounds[r - 1], new_snap[r - 1])
         wrong = sum(1 for i in range(n) if flags[i] == 3 and val[i] != ql[i])
         unknown = sum(1 for i in range(n) if H[i] is UNK)
         same = H == Hprev and new_snap == snap and new_carry == carry_ctx
@@ -75,8 +98,9 @@ def main():
     for name, data in cases.items():
         q = data[:data.size // 4 * 4].view(np.uint32)
         for nruns in (4, 16, 64):
-            hist = iterate(q, nruns)
-            print(f"{name:6s} {q.size:7d} quads {nruns:3d} runs: rounds {len(hist):3d}; (unknown hashes, wrong predicted values) per round: {hist[:12]}{' ...' if len(hist) > 12 else ''}")
+            for sweep in (False, True):
+                hist = iterate(q, nruns, sweep=sweep)
+                print(f"{name:6s} {q.size:7d} quads {nruns:3d} runs, carry sweep {'on ' if sweep else 'off'}: rounds {len(hist):3d}; (unknown hashes, wrong predicted values) per round: {hist[:8]}{' ...' if len(hist) > 8 else ''}")
 
 
 if __name__ == "__main__":

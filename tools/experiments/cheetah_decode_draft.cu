@@ -3,7 +3,8 @@
 // STATUS: compiles for sm_100a (nvcc -c), has NEVER RUN. It is not part of the library build (density_b200/build.py) and nothing
 // imports it. The algorithm of every pass is pinned by a Python model that reproduces the reference on dickens:
 //   pass 1  chunk-map values          tools/proto_cheetah_decode_chunkmap.py   (transfer functions per run and bucket, fold, concrete pass)
-//   pass 2  contexts by iteration     tools/proto_cheetah_decode_keyiter.py / _np.py  (10 rounds on 8.4 M quads, sparse after round 2)
+//   pass 2  predicted values          tools/proto_cheetah_decode_runs_gs.py   (in order inside a run + previous-round snapshots + unknown
+//                                     propagation + carry sweep: 3-5 rounds on text / zeros / mixed for any run count)
 //   why     PREDICTED quads never change the prediction table's values: tools/proto_cheetah_decode_hashchain.py
 // Reference semantics: /root/reference/src/algorithms/cheetah/cheetah.rs:67-103 (decode_plain / decode_map_a / decode_map_b /
 // decode_predicted) driven by /root/reference/src/codec/codec.rs:82-126.
@@ -168,118 +169,125 @@ cd_cmap_values(const uint32_t* __restrict__ f0, const uint32_t* __restrict__ f1,
     }
 }
 
-// ---- pass 2: predicted values by global iteration on the contexts -------------------------------------------------------------------
-// value(predicted quad i) = value of the latest non-predicted quad j < i with context_j == context_i (0 if none), context = hash of the
-// previous ENCODED quad (copy-mode blocks are skipped by the chain). Hin[] holds the current hash estimates (exact for non-predicted
-// quads, H_UNKNOWN or a guess for predicted ones); one round writes Hout[] for the predicted quads from a previous-occurrence pass
-// under those estimates. Entry per (run, context): {value, epoch, 1 + index of the run's first read before any write, -}.
-__global__ void cd_ctx0(const uint32_t* __restrict__ cpm, const uint32_t* __restrict__ Hin, uint32_t nruns, uint64_t ntiles, uint32_t* __restrict__ ctx0) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nruns) return;
-    uint64_t b = run_block_begin(r, nruns, ntiles);
-    uint32_t c = 0;                                            // last_hash starts as 0 (cheetah.rs:54)
-    while (b > 0) {
-        --b;
-        if ((cpm[b >> 5] >> (b & 31)) & 1u) continue;
-        c = Hin[b * 32 + 31];                                  // may be H_UNKNOWN: then the run's first context is unknown this round
-        break;
-    }
-    ctx0[r] = c;
-}
-
+// ---- pass 2: predicted values -----------------------------------------------------------------------------------------------------
+// The variant to build (tools/proto_cheetah_decode_runs_gs.py: 4-5 rounds on text / zeros / mixed for any run count):
+//   * a warp walks its run IN ORDER, so a chain of consecutive predicted quads advances through the whole run within one round;
+//   * value(predicted quad) = value of the latest non-predicted quad with the same context: in-warp predecessor, else the run's
+//     table (context written earlier in this run), else the SNAPSHOT of the context folded in the previous round, else UNKNOWN;
+//   * unknown propagates and never writes: an unknown hash makes the next context unknown, a non-predicted quad with an unknown
+//     context skips its table write this round;
+//   * after the round: snapshots refolded from the runs' tables on top of the zero table (cheetah.rs:53), the first context of every
+//     run = last hash of the run before it (cd_pred_carry, which also chases through runs of predicted quads only).
+// Entry per (run, context): {value, epoch, -, -}. snap[run][ctx] = value the context holds when the run starts; snap_valid[run].
 __global__ void __launch_bounds__(RP_WARPS * 32)
 cd_pred_round(const uint32_t* __restrict__ f0, const uint32_t* __restrict__ f1, const uint32_t* __restrict__ cpm, const uint32_t* __restrict__ val,
-              const uint32_t* __restrict__ Hin, uint64_t nblocks, uint32_t nruns, uint64_t ntiles, const uint32_t* __restrict__ ctx0,
-              uint4* __restrict__ ent_all, uint32_t epoch, uint32_t* __restrict__ pval /* values of the predicted quads */,
-              uint32_t* __restrict__ Hout, uint32_t* __restrict__ changed) {
+              const uint32_t* __restrict__ Hn /* hashes of the non-predicted quads (pass 1) */, uint64_t nblocks, uint32_t nruns, uint64_t ntiles,
+              const uint32_t* __restrict__ ctx0 /* first context per run or H_UNKNOWN */, const uint32_t* __restrict__ snap,
+              const uint32_t* __restrict__ snap_valid, uint4* __restrict__ ent_all, uint32_t epoch,
+              uint32_t* __restrict__ pval, uint32_t* __restrict__ pknown /* bit per quad: predicted value known */,
+              uint32_t* __restrict__ run_last_h, uint32_t* __restrict__ changed) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (r >= nruns) return;
     uint4* __restrict__ ent = ent_all + (size_t)r * 65536;
+    const uint32_t* __restrict__ sn = snap + (size_t)r * 65536;
+    const bool have_snap = snap_valid[r] != 0;
     const uint64_t b0 = run_block_begin(r, nruns, ntiles);
     uint64_t b1 = run_block_begin(r + 1, nruns, ntiles);
     if (b1 > nblocks) b1 = nblocks;
     uint32_t last_h = ctx0[r];
     uint32_t any_change = 0;
     for (uint64_t b = b0; b < b1; ++b) {
-        if ((cpm[b >> 5] >> (b & 31)) & 1u) continue;
+        if ((cpm[b >> 5] >> (b & 31)) & 1u) continue;                            // copy-mode block: the context chain skips it
         const uint32_t flag = ((f0[b] >> lane) & 1u) | (((f1[b] >> lane) & 1u) << 1);
         const bool pred = flag == 3;
-        const uint32_t hi = Hin[b * 32 + lane];
-        const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, hi, 1);
-        const uint32_t ctx = lane ? hp : last_h;                                 // H_UNKNOWN propagates: quad inactive this round
-        last_h = __shfl_sync(0xFFFFFFFFu, hi, 31);
-        const bool active = ctx != H_UNKNOWN;
-        const uint32_t v = pred ? 0u : val[b * 32 + lane];
-        uint4 e = make_uint4(0, 0, 0, 0);
-        if (active) e = __ldcg(&ent[ctx]);
-        const uint32_t key = active ? ctx : 0x10000u + lane;
+        uint32_t h = pred ? H_UNKNOWN : Hn[b * 32 + lane];                       // my hash; predicted lanes fill it in below
+        uint32_t v = pred ? 0u : val[b * 32 + lane];
+        bool known = !pred;
+        // predicted lanes in order: everything below the current one already has its hash (or is unknown for good this round)
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, pred);
+        while (todo) {
+            const int p = __ffs(todo) - 1; todo &= todo - 1;
+            const uint32_t hprev = __shfl_sync(0xFFFFFFFFu, h, p ? p - 1 : 0);
+            const uint32_t cp = p ? hprev : last_h;                              // context of lane p
+            // contexts of the lanes below p (all final by now)
+            const uint32_t hb = __shfl_up_sync(0xFFFFFFFFu, h, 1);
+            const uint32_t myc = lane ? hb : last_h;
+            const uint32_t wr = __ballot_sync(0xFFFFFFFFu, (int)lane < p && !pred && myc != H_UNKNOWN && myc == cp);
+            uint32_t got = 0; bool ok = false;
+            if (cp != H_UNKNOWN) {
+                if (wr) { got = __shfl_sync(0xFFFFFFFFu, v, 31 - __clz(wr)); ok = true; }
+                else {
+                    uint4 e = make_uint4(0, 0, 0, 0);
+                    if ((int)lane == p) e = __ldcg(&ent[cp]);
+                    const uint32_t ey = __shfl_sync(0xFFFFFFFFu, e.y, p), ex = __shfl_sync(0xFFFFFFFFu, e.x, p);
+                    if (ey == epoch) { got = ex; ok = true; }
+                    else if (have_snap) { uint32_t sv = 0; if ((int)lane == p) sv = sn[cp]; got = __shfl_sync(0xFFFFFFFFu, sv, p); ok = true; }
+                }
+            } else {
+                (void)__shfl_sync(0xFFFFFFFFu, v, 0);                            // keep the shuffle pattern uniform
+            }
+            if ((int)lane == p) { known = ok; if (ok) { v = got; h = prod_hash(hash_prod(got)); } }
+        }
+        // table writes: the last non-predicted lane of every KNOWN context leaves its value (cheetah.rs:75,84,96: pred[last_hash] = quad)
+        const uint32_t hb = __shfl_up_sync(0xFFFFFFFFu, h, 1);
+        const uint32_t myc = lane ? hb : last_h;
+        const bool writer = !pred && myc != H_UNKNOWN;
+        const uint32_t key = writer ? myc : 0x10000u + lane;
         const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
-        // latest WRITER (non-predicted lane) below me in my group
-        const uint32_t writers = __ballot_sync(0xFFFFFFFFu, active && !pred);
-        const uint32_t wl = grp & writers & lanemask_lt();
-        const int wsrc = wl ? 31 - __clz(wl) : 0;
-        const uint32_t wv = __shfl_sync(0xFFFFFFFFu, v, wsrc);
-        const bool touched = e.y == epoch;                                       // the run has written this context before this step
-        uint32_t got = 0; bool have = false;
-        if (active && pred) {
-            if (wl) { got = wv; have = true; }
-            else if (touched) { got = e.x; have = true; }
-        }
-        // first reads of a context the run has not written yet are left to the fold: chain them per context through the entry
-        // (z = 1 + index of the first such read; every later unresolved read of the context gets the same carried-in value, so
-        //  the fold only needs the context -> value map and a second sweep: see cd_pred_fold)
-        if (active && pred && !have) pval[b * 32 + lane] = 0x80000000u | ctx;    // marker: "carry-in of context ctx", patched by the fold sweep
-        else if (active && pred) pval[b * 32 + lane] = got;
-        // the group's last writer leaves its value
-        const uint32_t gw = grp & writers;
-        if (active && !pred && (gw & lanemask_gt()) == 0) ent[ctx] = make_uint4(v, epoch, 0u, 0u);
-        // new hash estimate of my predicted quad (unknown if it waits for the fold)
+        if (writer && (grp & lanemask_gt()) == 0) ent[myc] = make_uint4(v, epoch, 0u, 0u);
+        // results of the predicted lanes
+        const uint32_t kn = __ballot_sync(0xFFFFFFFFu, pred && known);
         if (pred) {
-            const uint32_t nh = (active && have) ? prod_hash(hash_prod(got)) : H_UNKNOWN;
-            Hout[b * 32 + lane] = nh;
-            any_change |= nh != hi;
-        } else {
-            Hout[b * 32 + lane] = hi;
+            const uint32_t old = pval[b * 32 + lane];
+            const bool was = (pknown[b] >> lane) & 1u;
+            if (known) { pval[b * 32 + lane] = v; any_change |= (!was || old != v); }
+            else any_change |= was;
         }
+        if (lane == 0) pknown[b] = kn;
+        last_h = __shfl_sync(0xFFFFFFFFu, h, 31);
         __syncwarp();
     }
+    if (lane == 0) run_last_h[r] = last_h;
     if (__any_sync(0xFFFFFFFFu, any_change) && lane == 0) atomicOr(changed, 1u);
 }
 
-// fold: carry[run][ctx] = value the context holds when the run starts (0 at the stream start, cheetah.rs:53)
-__global__ void cd_pred_fold(uint32_t nruns, const uint4* __restrict__ ent_all, uint32_t epoch, uint32_t* __restrict__ carry) {
+// fold: snap[run][ctx] for the NEXT round = value the context holds when the run starts (zero table at the stream start, cheetah.rs:53)
+__global__ void cd_pred_fold(uint32_t nruns, const uint4* __restrict__ ent_all, uint32_t epoch, uint32_t* __restrict__ snap,
+                             uint32_t* __restrict__ snap_valid) {
     const uint32_t ctx = blockIdx.x * blockDim.x + threadIdx.x;
     if (ctx >= 65536) return;
     uint32_t c = 0;
     for (uint32_t r = 0; r < nruns; ++r) {
-        carry[(size_t)r * 65536 + ctx] = c;
+        snap[(size_t)r * 65536 + ctx] = c;
         const uint4 e = ent_all[(size_t)r * 65536 + ctx];
         if (e.y == epoch) c = e.x;
     }
+    if (ctx == 0) for (uint32_t r = 0; r < nruns; ++r) snap_valid[r] = 1;       // from round 2 on every run has a snapshot
 }
-// sweep: patch the reads that waited for the carry-in (they can only be reads BEFORE the run's first write of the context, so the
-// carried-in value is the answer) and give their successors a hash estimate
-__global__ void cd_pred_patch(const uint32_t* __restrict__ f0, const uint32_t* __restrict__ f1, uint64_t nblocks, uint32_t nruns, uint64_t ntiles,
-                              const uint32_t* __restrict__ carry, uint32_t* __restrict__ pval, const uint32_t* __restrict__ Hin,
-                              uint32_t* __restrict__ Hout, uint32_t* __restrict__ changed) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nblocks * 32) return;
-    const uint64_t b = i >> 5; const uint32_t lane = i & 31;
-    const uint32_t flag = ((f0[b] >> lane) & 1u) | (((f1[b] >> lane) & 1u) << 1);
-    if (flag != 3) return;
-    const uint32_t pv = pval[i];
-    if (!(pv & 0x80000000u) || Hout[i] != H_UNKNOWN) return;   // NOTE(draft): a real value with bit 31 set collides with the marker —
-                                                               // the final version needs a separate "waiting" bit plane
-    // which run am I in? runs are whole tiles: binary search over run_block_begin would do; the draft recomputes it linearly
-    uint32_t r = (uint32_t)(((b / TILE_B) * (uint64_t)nruns) / ntiles);
-    while (r + 1 < nruns && run_block_begin(r + 1, nruns, ntiles) <= b) ++r;
-    while (r > 0 && run_block_begin(r, nruns, ntiles) > b) --r;
-    const uint32_t v = carry[(size_t)r * 65536 + (pv & 0xFFFFu)];
-    pval[i] = v;
-    const uint32_t nh = prod_hash(hash_prod(v));
-    Hout[i] = nh;
-    if (nh != Hin[i]) atomicOr(changed, 1u);
+
+// first context of every run for the next round: last hash of the run before it; a run of predicted quads only is a chase of
+// (run length) links x -> hash(snap[x]) on a static table, cut short at a fixed point / cycle
+// (one thread: R steps; `allpred[r]` = number of encoded quads of run r if they are all predicted, else 0 — from the flag planes)
+__global__ void cd_pred_carry(uint32_t nruns, const uint32_t* __restrict__ run_last_h, const uint32_t* __restrict__ allpred,
+                              const uint32_t* __restrict__ snap, uint32_t* __restrict__ ctx0) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t c = 0;                                            // last_hash starts as 0 (cheetah.rs:54)
+    for (uint32_t r = 0; r < nruns; ++r) {
+        ctx0[r] = c;
+        uint32_t e = run_last_h[r];
+        if (e == H_UNKNOWN && c != H_UNKNOWN && allpred[r]) {
+            const uint32_t* __restrict__ sn = snap + (size_t)r * 65536;
+            uint32_t x = c, steps = allpred[r], k = 0, tort = c, lam = 0, power = 1;      // Brent's cycle detection
+            while (k < steps) {
+                x = prod_hash(hash_prod(sn[x])); ++k; ++lam;
+                if (x == tort) { const uint32_t left = steps - k; k = steps - (left % lam); lam = 0; tort = x; power = 1; continue; }
+                if (lam == power) { tort = x; power <<= 1; lam = 0; }
+            }
+            e = x;
+        }
+        c = e;
+    }
 }
 
 // after the last round: out[] of the predicted quads
@@ -296,11 +304,12 @@ __global__ void cd_pred_commit(const uint32_t* __restrict__ f0, const uint32_t* 
 // Host driver sketch (rounds until `changed` stays 0; the verdict is read by the host between batches of rounds, or the round
 // kernels are gated on it as the encoder's stages are):
 //   cd_unpack -> cd_cmap_transfer -> cd_cmap_fold -> cd_cmap_values
-//   repeat: cd_ctx0 -> cd_pred_round(Hin -> Hout) -> cd_pred_fold -> cd_pred_patch -> swap(Hin, Hout)   [fresh epoch per round]
+//   round 1: ctx0 = {0, H_UNKNOWN, ...}, snap_valid = {1, 0, ...} (run 0 starts from the zero table), pknown = 0
+//   repeat: cd_pred_round -> cd_pred_fold -> cd_pred_carry     [fresh epoch per round; stop when `changed` stays 0 and no quad is unknown]
 //   cd_pred_commit; tail loop (codec.rs:102-123) in order from the folded tables as in chameleon_decode.cu::dec_tail
-// Open points: (1) the 0x80000000 marker (see NOTE); (2) in cd_pred_round a writer whose own context is unknown is skipped this
-// round (round 1 of the model) — correct at the fixed point, but the convergence check must also cover "no H_UNKNOWN left";
-// (3) later rounds touch < 0.1 % of the quads (model): restrict them to the runs that saw a change.
+// Open points: (1) the Brent loop above is untested (the model uses a dictionary of visited states); (2) later rounds touch < 0.1 % of
+// the quads (model): restrict them to the runs whose snapshot or first context changed; (3) Lion: 5 values per context
+// (tools/proto_lion_decode_full.py), same structure.
 
 }  // namespace cheedec
 }  // namespace dns

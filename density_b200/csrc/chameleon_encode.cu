@@ -41,26 +41,25 @@ namespace cham {
 constexpr int FP_THREADS = 1024;
 constexpr int FP_QPT = 4;                          // quads per thread per tile
 constexpr int TILE_Q = FP_THREADS * FP_QPT;        // 4096 quads = 16 KiB = 64 blocks
-constexpr int SIDE_N = 8192;                       // first-misser table (u32), indexed by hash & (SIDE_N-1)
+constexpr int SIDE_N = 4096;                       // first-misser table (u32), indexed by hash & (SIDE_N-1)
 constexpr uint32_t SIDE_EMPTY = 0xFFFFFFFFu;
 
-constexpr int CLS_N = 32;                          // slow-path classes: class = hash >> 11, one warp each
+constexpr int CLS_N = 32;                          // exact-path classes: class = hash >> 11, one warp each
 constexpr int CLS_CAP = 128;                       // entries per class list; overflow -> in-order tile fallback
 
-// Compacted per-tile record of a misser (or of a hit member that turned out to need the slow path):
+// Per-tile record of a quad that takes the exact path (a misser, or a hit candidate whose bucket a misser wrote before it):
 //   x = hash | fp << 16
-//   y = pos(12) | touched << 12 | slow << 13 | first << 14 | setter << 15 | old_fp << 16
-constexpr uint32_t R_TOUCHED = 1u << 12, R_SLOW = 1u << 13, R_FIRST = 1u << 14;
+//   y = pos(12) | touched << 12 | misser << 13 | old_fp << 16
+constexpr uint32_t R_TOUCHED = 1u << 12, R_MISSER = 1u << 13;
 
 struct FlagSmem {
     uint16_t tab[65536];          // fingerprint of the last quad seen in each bucket
     uint32_t vbit[2048];          // "bucket touched" for the one case tab cannot express (fingerprint 0)
-    uint32_t conf[2048];          // per-tile conflict bits (bucket interleaves different values)
     uint32_t side[SIDE_N];        // per-tile min over missers of (pos << 16 | hash)
-    uint2 rec[TILE_Q];            // records: missers (phase A) then slow hit members (phase C); quad staging in the fallback
-    uint16_t cls_list[CLS_N][CLS_CAP];  // record indices of the slow members of each class (unordered)
+    uint2 rec[TILE_Q];            // records of the exact path; quad staging in the in-order fallback
+    uint16_t cls_list[CLS_N][CLS_CAP];  // record indices of the members of each class (unordered)
     uint32_t cls_count[CLS_N];
-    uint32_t sigw[TILE_Q / 32];   // flag bits of the tile: word (w*4+j) = sub-row j of warp w
+    uint32_t sigw[2][TILE_Q / 32];   // flag bits of the tile (double buffered: tile t's words leave for HBM during tile t+1)
     uint32_t nrec;
     uint32_t unres_count;
     uint32_t cls_overflow;
@@ -85,8 +84,8 @@ __device__ __forceinline__ void append_unres(bool pred, uint32_t qidx_in_run, ui
 }
 
 // In-order walk of one whole tile by one warp, from the (restored) pre-tile dictionary. Fallback for tiles whose
-// class lists overflow (adversarial inputs: hundreds of interleaving quads in a handful of buckets).
-__device__ __noinline__ void tile_in_order(FlagSmem& S, const uint32_t* qs, uint32_t rem, uint32_t run_q0,
+// class lists overflow (adversarial inputs: hundreds of interleaving quads in a handful of buckets; the cold first tile of a run).
+__device__ __noinline__ void tile_in_order(FlagSmem& S, uint32_t* __restrict__ sig, const uint32_t* qs, uint32_t rem, uint32_t run_q0,
                                            uint2* __restrict__ unres_run, const uint8_t* __restrict__ cm_tile) {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t c = 0; c < TILE_Q / 32; ++c) {
@@ -109,11 +108,205 @@ __device__ __noinline__ void tile_in_order(FlagSmem& S, const uint32_t* qs, uint
             if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
         }
         const uint32_t fb = __ballot_sync(0xFFFFFFFFu, hit);
-        if (lane == 0) S.sigw[c] = fb;
+        if (lane == 0) sig[c] = fb;
         append_unres(valid && !lower && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
         __syncwarp();
     }
 }
+
+// One tile of the flag pass: four barrier-separated phases (validated against the in-order walk by tools/proto_tile_protocol_v2.py).
+//   A  every quad reads old = tab[h]; old == f -> hit candidate, else misser (~8 % on text). Missers are compacted into S.rec.
+//   B  missers publish f (racy on purpose: the bucket now holds SOME misser's value, which differs from the pre-tile value),
+//      atomicMin(side[h & (SIDE_N-1)], pos << 16 | h) (first misser of the bucket) and join their hash-class list.
+//   C  hit candidates re-read tab[h]: unchanged -> flag 1 (no misser in my bucket). Changed -> flag 1 if every misser of my bucket
+//      comes later (side slot), else the quad joins the class list as well.
+//   F  warp w resolves class w exactly: predecessor = same-bucket member with the largest smaller position, else the pre-tile value;
+//      the last member's value stays in the table. A misser without predecessor in a bucket this run has not touched yet cannot be
+//      decided here (the dictionary carried in from earlier runs is unknown): it goes to the run's unresolved list.
+// GENERIC = false: the tile is full and no block is in copy mode (the common case; no per-quad masks at all).
+template <bool GENERIC>
+__device__ __forceinline__ void flag_tile(FlagSmem& S, const uint32_t (&q)[FP_QPT], uint32_t rem, uint32_t run_q0, int buf,
+                                          uint2* __restrict__ unres_run, const uint8_t* __restrict__ cm_tile) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t pos0 = warp * 128 + lane;
+    uint32_t h[FP_QPT], f[FP_QPT];
+    uint32_t actmask = 0xFu;     // bit j: my sub-row j quad exists and its block is not in copy mode
+    if (GENERIC) {
+        uint32_t cp = 0;         // bit 0/1: block 2*warp / 2*warp+1 of this tile is a copy-mode block
+        if (cm_tile) cp = (cm_tile[warp * 2] ? 1u : 0u) | (cm_tile[warp * 2 + 1] ? 2u : 0u);
+        actmask = 0;
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j)
+            if (pos0 + 32 * j < rem && !((cp >> (j >> 1)) & 1u)) actmask |= 1u << j;
+    }
+    // ---- phase A ----------------------------------------------------------------------------------------
+    uint32_t missmask = 0;
+    {
+        uint32_t old[FP_QPT], mb[FP_QPT], tot = 0;
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            const uint32_t p = hash_prod(q[j]);
+            h[j] = prod_hash(p);
+            f[j] = prod_fp(p, q[j]);
+            old[j] = S.tab[h[j]];
+        }
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            bool miss = old[j] != f[j];
+            if (f[j] == 0 && !miss) miss = !bit_test(S.vbit, h[j]);     // fingerprint 0 == "empty": the touched bit decides (rare)
+            if (GENERIC) miss = miss && ((actmask >> j) & 1u);
+            if (miss) missmask |= 1u << j;
+            mb[j] = __ballot_sync(0xFFFFFFFFu, miss);
+            tot += __popc(mb[j]);
+        }
+        if (tot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&S.nrec, tot);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j) {
+                if (missmask & (1u << j)) {
+                    const bool touched = old[j] != 0 || bit_test(S.vbit, h[j]);
+                    S.rec[base + __popc(mb[j] & lanemask_lt())] =
+                        make_uint2(h[j] | (f[j] << 16), (pos0 + 32 * j) | (touched ? R_TOUCHED : 0u) | R_MISSER | (old[j] << 16));
+                }
+                base += __popc(mb[j]);
+            }
+        }
+    }
+    __syncthreads();  // S1: all reads of tab / vbit precede the publishes; S.nrec = number of missers
+    const uint32_t nmiss = S.nrec;  // stable until phase C appends behind it
+
+    // ---- phase B: missers publish ---------------------------------------------------------------------------
+    #pragma unroll 1
+    for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+        const uint2 r = S.rec[i];
+        const uint32_t hh = r.x & 0xFFFFu;
+        S.tab[hh] = (uint16_t)(r.x >> 16);  // racy between different values on purpose
+        atomicMin(&S.side[hh & (SIDE_N - 1)], ((r.y & 0xFFFu) << 16) | hh);
+        const uint32_t c = hh >> 11;
+        const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
+        if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)i; else S.cls_overflow = 1;
+    }
+    __syncthreads();  // S2
+
+    // ---- phase C: hit candidates read back ---------------------------------------------------------------------
+    {
+        uint32_t fb[FP_QPT];
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            bool ok = false;
+            if ((!GENERIC || ((actmask >> j) & 1u)) && !(missmask & (1u << j))) {
+                ok = S.tab[h[j]] == f[j];
+                if (!ok) {
+                    const uint32_t pos = pos0 + 32 * j;
+                    const uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
+                    if ((slot & 0xFFFFu) == h[j] && pos < (slot >> 16)) {
+                        ok = true;  // every misser of my bucket comes after me
+                    } else {
+                        const uint32_t idx = atomicAdd(&S.nrec, 1u);
+                        S.rec[idx] = make_uint2(h[j] | (f[j] << 16), pos | R_TOUCHED | (f[j] << 16));
+                        const uint32_t c = h[j] >> 11;
+                        const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
+                        if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)idx; else S.cls_overflow = 1;
+                    }
+                }
+            }
+            fb[j] = __ballot_sync(0xFFFFFFFFu, ok);
+        }
+        if (lane < FP_QPT) S.sigw[buf][warp * FP_QPT + lane] = lane == 0 ? fb[0] : lane == 1 ? fb[1] : lane == 2 ? fb[2] : fb[3];
+    }
+    __syncthreads();  // S3: class lists complete
+
+    // ---- phase F: exact resolution of the listed quads ------------------------------------------------------------
+    if (S.cls_overflow) {
+        // restore the pre-tile dictionary (only missers wrote), clear the per-tile state, walk the tile in order
+        #pragma unroll 1
+        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+            const uint2 r = S.rec[i];
+            S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
+            S.side[(r.x & 0xFFFFu) & (SIDE_N - 1)] = SIDE_EMPTY;
+        }
+        if (tid < CLS_N) S.cls_count[tid] = 0;
+        __syncthreads();
+        uint32_t* qs = reinterpret_cast<uint32_t*>(S.rec);
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) qs[pos0 + 32 * j] = q[j];
+        if (tid == 0) { S.nrec = 0; S.cls_overflow = 0; }
+        __syncthreads();
+        if (warp == 0) tile_in_order(S, S.sigw[buf], qs, rem, run_q0, unres_run, cm_tile);
+    } else {
+        const uint32_t n = S.cls_count[warp];
+        const uint16_t* __restrict__ lst = S.cls_list[warp];
+        if (n != 0 && n <= 32) {
+            // the whole class in one warp: same-bucket groups from match_any, predecessor by a walk over the (small) group
+            const bool valid = lane < n;
+            uint32_t pos = 0, hh = 0x10000u + lane, ff = 0, oldv = 0, fl = 0;
+            if (valid) {
+                const uint2 d = S.rec[lst[lane]];
+                hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & 0xFFFu; fl = d.y; oldv = d.y >> 16;
+            }
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, hh);
+            uint32_t others = grp & ~(1u << lane);
+            int best = -1; uint32_t bestf = 0; bool later = false;
+            while (__any_sync(0xFFFFFFFFu, others != 0)) {
+                const int src = others ? __ffs(others) - 1 : (int)lane;
+                const uint32_t pk = __shfl_sync(0xFFFFFFFFu, pos, src), fk = __shfl_sync(0xFFFFFFFFu, ff, src);
+                if (others) {
+                    if (pk < pos && (int)pk > best) { best = (int)pk; bestf = fk; }
+                    later |= pk > pos;
+                    others &= others - 1;
+                }
+            }
+            const bool touched = (fl & R_TOUCHED) != 0;
+            const bool hit = valid && (best >= 0 ? (bestf == ff) : (touched && oldv == ff));
+            if (hit) atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
+            if (valid && !later) {
+                S.tab[hh] = (uint16_t)ff;
+                if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+            }
+            if (valid && (fl & R_MISSER)) S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
+            append_unres(valid && best < 0 && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
+        } else if (n != 0) {
+            #pragma unroll 1
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < n;
+                uint32_t pos = 0, hh = 0xFFFFFFFFu, ff = 0, oldv = 0, fl = 0;
+                if (valid) {
+                    const uint2 d = S.rec[lst[i]];
+                    hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & 0xFFFu; fl = d.y; oldv = d.y >> 16;
+                }
+                int best = -1; uint32_t bestf = 0; bool later = false;
+                #pragma unroll 1
+                for (uint32_t k = 0; k < n; ++k) {
+                    const uint2 dk = S.rec[lst[k]];      // broadcast reads
+                    const uint32_t pk = dk.y & 0xFFFu;
+                    if ((dk.x & 0xFFFFu) == hh) {
+                        if (pk < pos && (int)pk > best) { best = (int)pk; bestf = dk.x >> 16; }
+                        later |= pk > pos;
+                    }
+                }
+                const bool touched = (fl & R_TOUCHED) != 0;
+                const bool hit = valid && (best >= 0 ? (bestf == ff) : (touched && oldv == ff));
+                if (hit) atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
+                if (valid && !later) {
+                    S.tab[hh] = (uint16_t)ff;
+                    if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                }
+                if (valid && (fl & R_MISSER)) S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
+                append_unres(valid && best < 0 && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) S.cls_count[warp] = 0;
+        if (tid == 0) S.nrec = 0;
+    }
+    __syncthreads();  // S4: dictionary final for this tile, sigw[buf] final
+}
+
+// run r owns the tiles [run_tile_begin(r), run_tile_begin(r + 1))
+__host__ __device__ __forceinline__ uint64_t run_tile_begin(uint32_t r, uint32_t nruns, uint32_t tiles_total) { return (uint64_t)r * tiles_total / nruns; }
 
 __global__ void __launch_bounds__(FP_THREADS, 1)
 cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_total, uint32_t nruns,
@@ -129,8 +322,8 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
     FlagSmem& S = *reinterpret_cast<FlagSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t run = blockIdx.x;
-    const uint64_t t_begin = (uint64_t)run * tiles_total / nruns;
-    const uint64_t t_end = (uint64_t)(run + 1) * tiles_total / nruns;
+    const uint64_t t_begin = run_tile_begin(run, nruns, tiles_total);
+    const uint64_t t_end = run_tile_begin(run + 1, nruns, tiles_total);
     uint2* __restrict__ unres_run = unres + (size_t)run * 65536;
     const uint32_t pos0 = warp * 128 + lane;  // position of my sub-row 0 quad inside a tile; sub-row j adds 32*j
     // run-relative 32-bit geometry (a run is < 2^32 quads): keeps 64-bit compares out of the tile loop
@@ -149,7 +342,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         #pragma unroll 1
         for (uint32_t i = tid; i < 65536 * 2 / 16; i += FP_THREADS) t4[i] = z;
         #pragma unroll 1
-        for (uint32_t i = tid; i < 2048; i += FP_THREADS) { S.vbit[i] = 0; S.conf[i] = 0; }
+        for (uint32_t i = tid; i < 2048; i += FP_THREADS) S.vbit[i] = 0;
         #pragma unroll 1
         for (uint32_t i = tid; i < SIDE_N; i += FP_THREADS) S.side[i] = SIDE_EMPTY;
         if (tid < CLS_N) S.cls_count[tid] = 0;
@@ -162,226 +355,33 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 #pragma unroll
     for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < run_quads) ? ld_stream_u32(rin + pos0 + 32 * j) : 0u;
 
-#ifdef DNS_PHASE_TIMING
-    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define DNS_PH(k) { long long tn = clock64(); ph[k] += tn - tprev; tprev = tn; }
-#else
-#define DNS_PH(k)
-#endif
     #pragma unroll 1
     for (uint32_t lt = 0; lt < ntile_run; ++lt) {
-        uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT];
+        uint32_t q[FP_QPT];
         const uint32_t run_q0 = lt * TILE_Q;                                  // first quad of the tile, relative to the run
         const uint32_t left = run_q0 < run_quads ? run_quads - run_q0 : 0u;   // quads left in the run from here
         const uint32_t rem = left < (uint32_t)TILE_Q ? left : (uint32_t)TILE_Q;
 #pragma unroll
         for (int j = 0; j < FP_QPT; ++j) q[j] = nxt[j];
-        {   // prefetch next tile (register double buffer; consumed one full tile later)
+        if (left >= 2u * TILE_Q) {   // prefetch the next tile (register double buffer; consumed one full tile later)
+            const uint32_t* __restrict__ np = rin + run_q0 + TILE_Q + pos0;
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j) nxt[j] = ld_stream_u32(np + 32 * j);
+        } else {
             const uint32_t nleft = left > (uint32_t)TILE_Q ? left - TILE_Q : 0u;
             const uint32_t* __restrict__ np = rin + run_q0 + TILE_Q + pos0;
 #pragma unroll
             for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nleft) ? ld_stream_u32(np + 32 * j) : 0u;
         }
+        // the previous tile's flag words leave for HBM while this tile is being worked on (workspace is sized in whole tiles)
+        if (lt > 0 && tid < TILE_Q / 32) rsig[(lt - 1) * (TILE_Q / 32) + tid] = S.sigw[(lt - 1) & 1][tid];
 
-        uint32_t actmask = 0;     // bit j: my sub-row j quad exists and its block is not in copy mode
-        {
-            uint32_t cp = 0;      // bit 0/1: block 2*warp / 2*warp+1 of this tile is a copy-mode block
-            if (rcm) cp = (rcm[lt * 64 + warp * 2] ? 1u : 0u) | (rcm[lt * 64 + warp * 2 + 1] ? 2u : 0u);
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j)
-                if (pos0 + 32 * j < rem && !((cp >> (j >> 1)) & 1u)) actmask |= 1u << j;
-        }
-        // ---- phase A: read the pre-tile dictionary; compact the missers into S.rec --------------------
-        uint32_t missmask = 0;    // bit j: my sub-row j quad missed
-        {
-            uint32_t old[FP_QPT], tch = 0;
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j) {
-                const uint32_t p = hash_prod(q[j]);
-                h[j] = prod_hash(p);
-                f[j] = prod_fp(p, q[j]);
-                old[j] = S.tab[h[j]];
-            }
-            uint32_t mb[FP_QPT], tot = 0;
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j) {
-                bool touched = old[j] != 0;
-                if (!touched) touched = bit_test(S.vbit, h[j]);
-                if (touched) tch |= 1u << j;
-                const bool miss = ((actmask >> j) & 1u) && !(touched && old[j] == f[j]);
-                if (miss) missmask |= 1u << j;
-                mb[j] = __ballot_sync(0xFFFFFFFFu, miss);
-                tot += __popc(mb[j]);
-            }
-            if (tot) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&S.nrec, tot);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-#pragma unroll
-                for (int j = 0; j < FP_QPT; ++j) {
-                    if (missmask & (1u << j))
-                        S.rec[base + __popc(mb[j] & lanemask_lt())] =
-                            make_uint2(h[j] | (f[j] << 16), (pos0 + 32 * j) | ((tch >> j) & 1u ? R_TOUCHED : 0u) | (old[j] << 16));
-                    base += __popc(mb[j]);
-                }
-            }
-        }
-        __syncthreads();  // S1: all reads of tab/vbit precede the publishes; S.nrec = number of missers
-        DNS_PH(0)
-        const uint32_t nmiss = S.nrec;  // stable until phase C appends behind it
-
-        // ---- phase B: missers publish ---------------------------------------------------------------
-        #pragma unroll 1
-        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
-            const uint2 r = S.rec[i];
-            const uint32_t hh = r.x & 0xFFFFu;
-            S.tab[hh] = (uint16_t)(r.x >> 16);  // racy between different values on purpose
-            atomicMin(&S.side[hh & (SIDE_N - 1)], ((r.y & 0xFFFu) << 16) | hh);
-        }
-        __syncthreads();  // S2
-        DNS_PH(1)
-
-        // ---- phase C: read back ----------------------------------------------------------------------
-        // hit members: the bucket still holds my value unless some misser published (its value differs from mine)
-#pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            const uint32_t pos = pos0 + 32 * j;
-            bool ok = false;
-            if (((actmask >> j) & 1u) && !(missmask & (1u << j))) {
-                ok = S.tab[h[j]] == f[j];
-                if (!ok) {
-                    const uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
-                    if ((slot & 0xFFFFu) == h[j] && pos < (slot >> 16)) {
-                        ok = true;  // every misser of my bucket comes after me
-                    } else {
-                        // slow hit member: join the records and my class list, raise the conflict bit
-                        const uint32_t idx = atomicAdd(&S.nrec, 1u);
-                        S.rec[idx] = make_uint2(h[j] | (f[j] << 16), pos | R_TOUCHED | (f[j] << 16));
-                        const uint32_t c = h[j] >> 11;
-                        const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
-                        if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)idx; else S.cls_overflow = 1;
-                        atomicOr(&S.conf[h[j] >> 5], 1u << (h[j] & 31));
-                    }
-                }
-            }
-            const uint32_t fb = __ballot_sync(0xFFFFFFFFu, ok);
-            if (lane == 0) S.sigw[warp * 4 + j] = fb;
-        }
-        // missers: do all missers of my bucket agree, and who is first?
-        #pragma unroll 1
-        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
-            const uint2 r = S.rec[i];
-            const uint32_t hh = r.x & 0xFFFFu;
-            const uint32_t slot = S.side[hh & (SIDE_N - 1)];
-            const uint32_t w = S.tab[hh];
-            uint32_t y = r.y;
-            if ((slot & 0xFFFFu) != hh || w != (r.x >> 16)) {   // foreign slot owner, or missers disagree
-                y |= R_SLOW;
-                atomicOr(&S.conf[hh >> 5], 1u << (hh & 31));
-            } else if (slot == (((r.y & 0xFFFu) << 16) | hh)) {
-                y |= R_FIRST;
-            }
-            if (y != r.y) S.rec[i].y = y;
-        }
-        __syncthreads();  // S3
-        DNS_PH(2)
-
-        // ---- phase D: missers classify ----------------------------------------------------------------
-        #pragma unroll 1
-        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
-            const uint2 r = S.rec[i];
-            const uint32_t hh = r.x & 0xFFFFu;
-            uint32_t y = r.y;
-            if (!(y & R_SLOW) && bit_test(S.conf, hh)) { y |= R_SLOW; S.rec[i].y = y; }
-            if (y & R_SLOW) {
-                const uint32_t c = hh >> 11;
-                const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
-                if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)i; else S.cls_overflow = 1;
-            } else if (!(y & R_FIRST)) {
-                const uint32_t pos = y & 0xFFFu;
-                atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));  // predecessor in the bucket is a misser with my value
-            }
-            S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
-        }
-        __syncthreads();  // S4
-        DNS_PH(3)
-
-        // ---- phase F ------------------------------------------------------------------------------------
-        S.conf[tid] = 0; S.conf[tid + FP_THREADS] = 0;   // all readers of the conflict bits are behind S4; next set in the next tile's phase C
-        if (S.cls_overflow) {
-            // restore the pre-tile dictionary (only missers wrote), clear the per-tile state, walk the tile in order
-            #pragma unroll 1
-            for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
-                const uint2 r = S.rec[i];
-                S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
-            }
-            if (tid < CLS_N) S.cls_count[tid] = 0;
-            __syncthreads();
-            uint32_t* qs = reinterpret_cast<uint32_t*>(S.rec);
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j) qs[pos0 + 32 * j] = q[j];
-            if (tid == 0) { S.nrec = 0; S.cls_overflow = 0; }
-            __syncthreads();
-            if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run, rcm ? rcm + lt * 64 : nullptr);
-        } else {
-            // first missers of agreeing buckets: genuine miss or unresolved first touch; deferred vbit; conflict-bit cleanup
-            #pragma unroll 1
-            for (uint32_t base = warp * 32; base < nmiss; base += FP_THREADS) {
-                const uint32_t i = base + lane;
-                uint2 r = make_uint2(0, 0);
-                if (i < nmiss) r = S.rec[i];
-                const uint32_t hh = r.x & 0xFFFFu;
-                const bool first = (i < nmiss) && (r.y & (R_FIRST | R_SLOW)) == R_FIRST;
-                if (first && (r.x >> 16) == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-                append_unres(first && !(r.y & R_TOUCHED), run_q0 + (r.y & 0xFFFu), hh, r.x >> 16, &S.unres_count, unres_run);
-            }
-            // slow members, warp w <- class w. In-order semantics per bucket: my predecessor is the member of my bucket
-            // with the largest smaller position; without one the pre-tile value decides. The last member's value stays.
-            const uint32_t n = S.cls_count[warp];
-            const uint16_t* __restrict__ lst = S.cls_list[warp];
-            #pragma unroll 1
-            for (uint32_t base = 0; base < n; base += 32) {
-                const uint32_t i = base + lane;
-                const bool valid = i < n;
-                uint32_t pos = 0, hh = 0xFFFFFFFFu, ff = 0, oldv = 0; bool touched = false;
-                if (valid) {
-                    const uint2 d = S.rec[lst[i]];
-                    hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & 0xFFFu; touched = (d.y & R_TOUCHED) != 0; oldv = d.y >> 16;
-                }
-                int best = -1; uint32_t bestf = 0; bool later = false;
-                #pragma unroll 1
-                for (uint32_t k = 0; k < n; ++k) {
-                    const uint2 dk = S.rec[lst[k]];      // broadcast reads
-                    const uint32_t pk = dk.y & 0xFFFu;
-                    if ((dk.x & 0xFFFFu) == hh) {
-                        if (pk < pos && (int)pk > best) { best = (int)pk; bestf = dk.x >> 16; }
-                        later |= pk > pos;
-                    }
-                }
-                const bool hit = valid && (best >= 0 ? (bestf == ff) : (touched && oldv == ff));
-                if (hit) atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));
-                if (valid && !later) {
-                    S.tab[hh] = (uint16_t)ff;
-                    if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-                }
-                append_unres(valid && best < 0 && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
-            }
-            __syncwarp();
-            if (lane == 0) S.cls_count[warp] = 0;
-            if (tid == 0) S.nrec = 0;
-        }
-        __syncthreads();  // S5: dictionary final for this tile, sigw final
-        DNS_PH(4)
-
-        if (tid < TILE_Q / 32) rsig[lt * (TILE_Q / 32) + tid] = S.sigw[tid];  // workspace is sized in whole tiles
-        // (the next iteration rewrites S.sigw only after two more barriers)
+        const int buf = (int)(lt & 1);
+        if (rcm != nullptr || rem < (uint32_t)TILE_Q) flag_tile<true>(S, q, rem, run_q0, buf, unres_run, rcm ? rcm + lt * 64 : nullptr);
+        else flag_tile<false>(S, q, rem, run_q0, buf, unres_run, nullptr);
     }
+    if (ntile_run > 0 && tid < TILE_Q / 32) rsig[(ntile_run - 1) * (TILE_Q / 32) + tid] = S.sigw[(ntile_run - 1) & 1][tid];
 
-#ifdef DNS_PHASE_TIMING
-    if (tid == 0 && run == 77) { const long long nt = (long long)ntile_run;
-        printf("run %u tiles %lld cycles/tile: A %lld B %lld C %lld D %lld F %lld  total %lld\n", run, nt,
-               ph[0] / nt, ph[1] / nt, ph[2] / nt, ph[3] / nt, ph[4] / nt, (ph[0] + ph[1] + ph[2] + ph[3] + ph[4]) / nt); }
-#endif
     // ---- export the run's last-writer table ---------------------------------------------------------
     #pragma unroll 1
     for (uint32_t i = tid; i < 65536; i += FP_THREADS) {
@@ -419,7 +419,7 @@ __global__ void cham_resolve(const uint2* __restrict__ unres, const uint32_t* __
     if (!gate_open(gate)) return;
     const uint32_t run = blockIdx.y;
     const uint32_t n = unres_count[run];
-    const uint64_t run_q0 = ((uint64_t)run * tiles_total / nruns) * TILE_Q;
+    const uint64_t run_q0 = run_tile_begin(run, nruns, tiles_total) * TILE_Q;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint2 e = unres[(size_t)run * 65536 + i];
         uint32_t c = carry[(size_t)run * 65536 + (e.y & 0xFFFFu)];
@@ -776,15 +776,70 @@ __global__ void __launch_bounds__(SCAN_T) scan_group_totals(const uint64_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Pass 2: emit. One CTA (256 threads) per tile of 64 blocks; warp w handles block pairs w, w+8, ...
+// Pass 2: emit. One CTA (256 threads) per tile of 64 blocks. Pure tile movement: 128-bit streaming loads of the 16 KiB input tile,
+// the tile's piece of the stream (<= 16.5 KiB) is assembled in shared memory at its final byte layout, and leaves as ONE bulk
+// asynchronous copy shared -> global (cp.async.bulk, the TMA engine's 1-D mode) for the 16-byte aligned middle plus a few 2-byte
+// stores for the ragged edges (the stream is only 2-byte aligned: block sizes are even, codec.rs:39-68).
 // ------------------------------------------------------------------------------------------------------
 constexpr int EM_THREADS = 256;
+constexpr int EM_STAGE = 64 * 264 + 32;   // largest tile (64 all-plain blocks) + alignment slack
 
+__device__ __forceinline__ uint4 ld_stream_u128(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void bulk_store_smem_to_global(void* gdst, const void* ssrc, uint32_t bytes) {   // 16-byte aligned, bytes % 16 == 0
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes to shared memory -> visible to the async proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until it has been read
+}
+
+// The quads of one thread: 4 consecutive quads of block `bl`, starting at quad k of the block. FULL: the tile has 64 whole blocks.
+template <bool FULL>
+__device__ __forceinline__ void emit_quads(uint8_t* __restrict__ st, const uint32_t* s_off, const uint32_t* s_sig, const uint8_t* s_copied,
+                                           const uint4 v, uint32_t u, uint32_t nvalid_tile /* quads of this tile that exist */) {
+    const uint32_t bl = u >> 4, k = (u & 15u) * 4;
+    const uint32_t qs[4] = {v.x, v.y, v.z, v.w};
+    uint32_t nv = 4;                                                   // how many of my four quads exist
+    if (!FULL) { const uint32_t first = u * 4; nv = nvalid_tile > first ? (nvalid_tile - first < 4 ? nvalid_tile - first : 4u) : 0u; }
+    uint8_t* p = st + s_off[bl];
+    if (s_copied[bl]) {                                                // copy-mode block: raw bytes (codec.rs:36)
+        p += 4 * k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (FULL || (uint32_t)j < nv) { st_u16(p + 4 * j, qs[j] & 0xFFFFu); st_u16(p + 4 * j + 2, qs[j] >> 16); }
+        return;
+    }
+    const uint32_t lo = s_sig[2 * bl], hi = s_sig[2 * bl + 1];
+    if (k == 0 && (FULL || nv > 0 || true)) {                          // signature, 8 bytes LE at the block start (codec.rs:24-26,40-41,67)
+        st_u16(p, lo & 0xFFFFu); st_u16(p + 2, lo >> 16); st_u16(p + 4, hi & 0xFFFFu); st_u16(p + 6, hi >> 16);
+    }
+    const uint32_t word = k < 32 ? lo : hi, kk = k & 31u;
+    const uint32_t before = (k < 32 ? 0u : (uint32_t)__popc(lo)) + __popc(word & ((1u << kk) - 1u));
+    const uint32_t fl = word >> kk;
+    p += 8 + 4 * k - 2 * before;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (FULL || (uint32_t)j < nv) {
+            const bool hit = (fl >> j) & 1u;
+            const uint32_t hsh = prod_hash(hash_prod(qs[j]));
+            st_u16(p, hit ? hsh : (qs[j] & 0xFFFFu));                  // chameleon.rs:97-98 / :92-93
+            if (!hit) st_u16(p + 2, qs[j] >> 16);
+            p += hit ? 2 : 4;
+        }
+    }
+}
+
+template <bool AL16>
 __global__ void __launch_bounds__(EM_THREADS)
 cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, const uint32_t* __restrict__ sigw_g,
           const uint8_t* __restrict__ copymap, int use_copymap_if_nonquiet, const Status* __restrict__ status,
           const uint32_t* __restrict__ tile_local, const uint64_t* __restrict__ group_off, uint8_t* __restrict__ out) {
     if (status->error) return;
+    __shared__ __align__(16) uint8_t s_stage[EM_STAGE];
     __shared__ uint32_t s_off[65];
     __shared__ uint32_t s_sig[128];
     __shared__ uint8_t s_copied[64];
@@ -794,21 +849,32 @@ cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, co
     const bool use_cm = copymap && (!use_copymap_if_nonquiet || status->nonquiet);
     const uint64_t tile_off = group_off[tile / SCAN_G] + tile_local[tile];
     const uint64_t nquads = nbytes / 4;
-    // Issue all 16 input loads of this thread first (4 block pairs x 4 sub-rows): the kernel is latency-bound on them otherwise.
-    uint32_t qv[16];
+    const uint64_t tq0 = (uint64_t)tile * 4096;
+    const bool full = tq0 + 4096 <= nquads;                            // 64 whole blocks (CTA-uniform)
+    const uint32_t nvalid_tile = full ? 4096u : (uint32_t)(nquads > tq0 ? nquads - tq0 : 0);
+    // all input loads of this thread first: 4 x 16 bytes, consecutive threads read consecutive 16-byte pieces
+    uint4 qv[4];
+    if (AL16 && full) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i) qv[i] = ld_stream_u128(in + tq0 + 4u * (i * EM_THREADS + tid));
+    } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint64_t gq = ((uint64_t)tile * 64 + (warp + 8 * i) * 2 + (j >> 1)) * 64 + (j & 1) * 32 + lane;
-            qv[i * 4 + j] = (gq < nquads) ? ld_stream_u32(in + gq) : 0u;
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t r = 4u * (i * EM_THREADS + tid);
+            const uint32_t* g = in + tq0 + r;
+            qv[i].x = (r + 0 < nvalid_tile) ? ld_stream_u32(g + 0) : 0u;
+            qv[i].y = (r + 1 < nvalid_tile) ? ld_stream_u32(g + 1) : 0u;
+            qv[i].z = (r + 2 < nvalid_tile) ? ld_stream_u32(g + 2) : 0u;
+            qv[i].w = (r + 3 < nvalid_tile) ? ld_stream_u32(g + 3) : 0u;
         }
     }
 
+    const uint64_t b_first = (uint64_t)tile * 64;
+    const uint32_t nb_tile = (uint32_t)((nblocks - b_first < 64) ? (nblocks - b_first) : 64);
     if (tid < 64) {
-        const uint64_t b = (uint64_t)tile * 64 + tid;
+        const uint64_t b = b_first + tid;
         uint32_t sz = 0, lo = 0, hi = 0; bool copied = false;
-        if (b < nblocks) {
+        if (tid < nb_tile) {
             copied = use_cm && copymap[b];
             lo = sigw_g[2 * b]; hi = sigw_g[2 * b + 1];
             sz = block_out_bytes(b, nbytes, __popc(lo) + __popc(hi), copied);
@@ -825,52 +891,50 @@ cham_emit(const uint32_t* __restrict__ in, uint64_t nbytes, uint64_t nblocks, co
     if (tid == 0) s_off[0] = 0;
     __syncthreads();
 
-    const uint8_t* in_b = reinterpret_cast<const uint8_t*>(in);
+    // the tile's bytes sit in s_stage at the same offset modulo 16 as in the output, so that whole 16-byte lines can leave as they are
+    uint8_t* const gdst = out + tile_off;
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+    uint8_t* const st = s_stage + a;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t bp = warp + 8 * i;
+        for (int i = 0; i < 4; ++i) emit_quads<true>(st, s_off, s_sig, s_copied, qv[i], i * EM_THREADS + tid, 4096u);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t q = qv[i * 4 + j];
-            const uint32_t bl = bp * 2 + (j >> 1);                   // block within tile
-            const uint64_t b = (uint64_t)tile * 64 + bl;
-            if (b >= nblocks) continue;                               // warp-uniform
-            const uint32_t k = (j & 1) * 32 + lane;                   // quad index within block
-            const uint64_t gq = b * 64 + k;
-            uint8_t* const bout = out + tile_off + s_off[bl];
-            if (s_copied[bl]) {
-                // copy-mode block: raw bytes (codec.rs:36)
-                const uint64_t boff = b * 256;
-                const uint32_t blen = (uint32_t)((nbytes - boff < 256) ? (nbytes - boff) : 256);
-                if (gq < nquads && k * 4 + 4 <= blen) {
-                    st_u16(bout + 4 * k, q & 0xFFFFu); st_u16(bout + 4 * k + 2, q >> 16);
-                }
-                if ((j & 1) == 1 && lane < (blen & 3u)) bout[(blen & ~3u) + lane] = in_b[boff + (blen & ~3u) + lane];
-                continue;
-            }
-            const uint32_t lo = s_sig[2 * bl], hi = s_sig[2 * bl + 1];
-            if ((j & 1) == 0 && lane < 4) {
-                // signature, 8 bytes LE at the block start (codec.rs:24-26,40-41,67)
-                st_u16(bout + 2 * lane, ((lane < 2 ? lo : hi) >> (16 * (lane & 1))) & 0xFFFFu);
-            }
-            if (gq < nquads) {
-                const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
-                const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
-                uint8_t* p = bout + 8 + 4 * k - 2 * before;
-                if (flag) {
-                    st_u16(p, prod_hash(hash_prod(q)));               // chameleon.rs:97-98
-                } else {
-                    st_u16(p, q & 0xFFFFu); st_u16(p + 2, q >> 16);  // chameleon.rs:92-93
-                }
-            }
-            // 1..3 raw tail bytes after the last quad of the final block (codec.rs:58-61)
-            if ((j & 1) == 1 && b == nblocks - 1 && lane < (uint32_t)(nbytes & 3)) {
-                const uint64_t boff = b * 256;
-                const uint32_t blen = (uint32_t)(nbytes - boff);
-                const uint32_t nq = blen >> 2;
-                uint8_t* p = bout + 8 + 4 * nq - 2 * (__popc(lo) + __popc(hi));
-                p[lane] = in_b[boff + (blen & ~3u) + lane];
-            }
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t u = i * EM_THREADS + tid;
+            if ((u >> 4) < nb_tile) emit_quads<false>(st, s_off, s_sig, s_copied, qv[i], u, nvalid_tile);
+        }
+        // 1..3 raw tail bytes after the last quad of the final block (codec.rs:58-61; copy mode: the rest of the raw block)
+        if ((nbytes & 3u) && b_first + nb_tile == nblocks && tid < (uint32_t)(nbytes & 3u)) {
+            const uint64_t b = nblocks - 1;
+            const uint32_t bl = nb_tile - 1;
+            const uint32_t blen = (uint32_t)(nbytes - b * 256);
+            const uint32_t nq = blen >> 2;
+            const uint32_t at = s_copied[bl] ? (blen & ~3u) : 8 + 4 * nq - 2 * (__popc(s_sig[2 * bl]) + __popc(s_sig[2 * bl + 1]));
+            st[s_off[bl] + at + tid] = reinterpret_cast<const uint8_t*>(in)[b * 256 + (blen & ~3u) + tid];
+        }
+    }
+    __syncthreads();
+
+    const uint32_t total = s_off[nb_tile];                              // bytes of this tile
+    const uint32_t end = a + total;
+    const uint32_t mid_lo = a ? 16u : 0u;                               // s_stage offsets of the 16-byte aligned middle [mid_lo, mid_hi)
+    const uint32_t mid_hi = end & ~15u;
+    const bool have_mid = mid_hi > mid_lo;
+    uint8_t* const gbase = gdst - a;                                    // 16-byte aligned
+    if (have_mid && tid == 0) bulk_store_smem_to_global(gbase + mid_lo, s_stage + mid_lo, mid_hi - mid_lo);
+    // ragged edges: [a, head_hi) in front of the middle and [mid_hi, end) behind it (everything when there is no aligned middle)
+    const uint32_t head_hi = have_mid ? mid_lo : end;
+    if (tid >= 32 && tid < 64) {
+        for (uint32_t o = a + 2 * (tid - 32); o < head_hi; o += 64) {
+            if (o + 2 <= head_hi) st_u16(gbase + o, *reinterpret_cast<const uint16_t*>(s_stage + o));
+            else gbase[o] = s_stage[o];
+        }
+    }
+    if (have_mid && tid >= 64 && tid < 96) {
+        for (uint32_t o = mid_hi + 2 * (tid - 64); o < end; o += 64) {
+            if (o + 2 <= end) st_u16(gbase + o, *reinterpret_cast<const uint16_t*>(s_stage + o));
+            else gbase[o] = s_stage[o];
         }
     }
 }
@@ -1059,10 +1123,16 @@ cudaError_t cham_phase2_finish(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), st, (uint64_t)cap, d_out_size);
     *launches += 2;
     if (ev) cudaEventRecord(ev[2], stream);
-    cham_emit<<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw,
-                                                 with_copy_map ? copymap : nullptr, 1, st,
-                                                 reinterpret_cast<uint32_t*>(ws + L.tile_local),
-                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) == 0)
+        cham_emit<true><<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw,
+                                                           with_copy_map ? copymap : nullptr, 1, st,
+                                                           reinterpret_cast<uint32_t*>(ws + L.tile_local),
+                                                           reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
+    else
+        cham_emit<false><<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw,
+                                                            with_copy_map ? copymap : nullptr, 1, st,
+                                                            reinterpret_cast<uint32_t*>(ws + L.tile_local),
+                                                            reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
     ++*launches;
     if (ev) cudaEventRecord(ev[3], stream);
     return cudaGetLastError();
@@ -1165,9 +1235,9 @@ cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8
     scan_group_totals<<<1, SCAN_T, 0, stream>>>(reinterpret_cast<uint64_t*>(ws + L.group_total), ngroups,
                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), st, (uint64_t)cap, d_out_size);
     ++*launches;
-    cham_emit<<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw, copymap, 0, st,
-                                                 reinterpret_cast<uint32_t*>(ws + L.tile_local),
-                                                 reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
+    cham_emit<false><<<ntiles, EM_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, nblocks, sigw, copymap, 0, st,
+                                                        reinterpret_cast<uint32_t*>(ws + L.tile_local),
+                                                        reinterpret_cast<uint64_t*>(ws + L.group_off), d_out);
     ++*launches;
     return cudaGetLastError();
 }

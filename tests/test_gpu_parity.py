@@ -468,3 +468,54 @@ def test_cheetah_lion_encode_paths(torch_cuda, codecs, alg, path, kind, nbytes):
     if path == 1 and n == 0 and kind in ("mixed", "dickens"):
         pytest.skip("copy map not settled by the parallel rounds (path 0 falls back to the in-order kernel)")
     assert n == want.size and (d_out[:n].cpu().numpy() == want).all()
+
+
+def _device_mixed(torch, synth, n):
+    """n bytes of the synthetic mixed text/binary corpus on the device, generated in 1 GiB pieces (region-aligned, so the pieces
+    concatenate to the same bytes as one call)."""
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    step = 1 << 30
+    for off in range(0, n, step):
+        k = min(step, n - off)
+        d[off:off + k] = synth.synth_mixed(k, device="cuda", first_region=off // synth.REGION)
+    return d
+
+
+def test_cheetah_full_size_1gib_text_bit_exact(torch_cuda, codecs):
+    """BASELINE.json configs[2] (encode half) at full size: Cheetah encode of the 1 GiB synthetic text, every byte against the oracle
+    (cheetah.rs:121-150 through codec.rs:34-80)."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    n = 1 << 30
+    d_in = synth.synth_text(n, device="cuda")
+    d_out = torch.zeros(codecs["cheetah"].safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("cheetah", d_in, d_out, d_sz, path=1)     # run-parallel encoder only: no in-order fallback
+    torch.cuda.synchronize()
+    m = int(d_sz.item())
+    want = oracle.encode("cheetah", d_in.cpu().numpy())
+    assert m == want.size
+    assert (d_out[:m].cpu().numpy() == want).all()
+
+
+def test_lion_full_size_4gib_mixed_bit_exact(torch_cuda, codecs):
+    """BASELINE.json configs[3] at full size: Lion encode of the 4 GiB mixed text/binary buffer (2^32 bytes: quad and byte offsets
+    cross 32 bits), every byte against the oracle (lion.rs:209-271 through codec.rs:34-80)."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    n = 1 << 32
+    if torch.cuda.mem_get_info()[0] < 40 * (1 << 30):
+        pytest.skip("needs 40 GiB of free device memory")
+    d_in = _device_mixed(torch, synth, n)
+    C = codecs["lion"]
+    d_out = torch.empty(C.safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    m = C.encode(d_in, d_out)                                             # lion_encode(): device pointers, synchronous (path 4)
+    data = d_in.cpu().numpy()
+    want, copied = oracle.encode("lion", data, return_copied=True)
+    assert copied > 0
+    assert m == want.size
+    got = d_out[:m].cpu().numpy()
+    for off in range(0, m, 1 << 28):                                      # compare in pieces: bounded temporaries
+        assert (got[off:off + (1 << 28)] == want[off:off + (1 << 28)]).all(), off

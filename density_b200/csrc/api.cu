@@ -50,7 +50,7 @@ struct DeviceCtx {
     bool ready = false;
     cudaStream_t stream = nullptr;     // for the synchronous host-pointer entry points (compute)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the pipelined host path
-    DevBuf ws, stage_in, stage_out, pipe_tables;
+    DevBuf ws, stage_in, stage_out, pipe_tables, dec_tables;
     DevBuf chee_tables[2][3];          // epoch-tagged run tables of the Cheetah / Lion encoders (zero at allocation, one entry format each)
     uint32_t chee_epoch = 0;
     uint64_t* h_sizes = nullptr;       // pinned, PIPE_MAX_CHUNKS entries
@@ -193,13 +193,36 @@ static int decode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
     const bool parallel_ok = alg == ALG_CHAMELEON && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 1) && !(reinterpret_cast<uintptr_t>(d_out) & 3);
     if (parallel_ok) {
         // parallel decoder; the exact in-order kernel is queued behind it and only runs when the stream has copy-mode blocks
-        const size_t pw = (cham_decode_workspace_bytes(n, c->num_sms) + 255) & ~(size_t)255;
+        const size_t pw = (cham_decode_workspace_bytes(n, cap, c->num_sms) + 255) & ~(size_t)255;
         e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg));
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
         uint32_t* d_nonquiet = reinterpret_cast<uint32_t*>(c->ws.p + pw);
         e = cham_decode_parallel(d_in, n, d_out, cap, c->ws.p, c->num_sms, d_out_size, d_nonquiet, stream, &launches);
         if (e == cudaSuccess && path != 1)
             e = scalar_decode(alg, d_in, n, d_out, cap, c->ws.p + pw + 256, d_out_size, stream, &launches, d_nonquiet);
+        g_launches += launches;
+        if (e != cudaSuccess) { set_error("decode launch", e); return DENSITY_B200_ECUDA; }
+        return DENSITY_B200_OK;
+    }
+    if (alg == ALG_CHEETAH && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 1) && !(reinterpret_cast<uintptr_t>(d_out) & 3)) {
+        // run-parallel Cheetah decoder (cl_decode.cu) + in-order tail; the exact in-order kernel is queued behind it and only runs if
+        // the context iteration did not settle within its round budget
+        const size_t pw = (chee_decode_workspace_bytes(n, cap, c->num_sms) + 255) & ~(size_t)255;
+        e = c->ws.ensure(pw + 256 + 2 * ((scalar_workspace_bytes(alg) + 255) & ~(size_t)255));
+        if (e == cudaSuccess) e = c->dec_tables.ensure(chee_decode_tables_bytes(n, c->num_sms) + 256);
+        if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+        uint32_t* d_fallback = reinterpret_cast<uint32_t*>(c->ws.p + pw);
+        uint8_t* tail_ws = c->ws.p + pw + 256;
+        uint8_t* scalar_ws = tail_ws + ((scalar_workspace_bytes(alg) + 255) & ~(size_t)255);
+        e = cudaMemsetAsync(tail_ws, 0, 256, stream);
+        if (e == cudaSuccess) e = chee_decode_parallel(d_in, n, d_out, cap, c->ws.p, c->dec_tables.p, tail_ws, c->num_sms, d_out_size, d_fallback, stream, &launches);
+        if (e == cudaSuccess) {
+            const void* cl_st = nullptr;
+            const void* b_st = chee_decode_status_ptr(c->ws.p, n, cap, c->num_sms, &cl_st);
+            e = scalar_decode_tail(alg, d_in, n, d_out, cap, tail_ws, b_st, cl_st, d_out_size, stream, &launches, d_fallback);
+        }
+        if (e == cudaSuccess && path != 1)
+            e = scalar_decode(alg, d_in, n, d_out, cap, scalar_ws, d_out_size, stream, &launches, d_fallback);
         g_launches += launches;
         if (e != cudaSuccess) { set_error("decode launch", e); return DENSITY_B200_ECUDA; }
         return DENSITY_B200_OK;
@@ -541,7 +564,7 @@ void density_b200_shutdown(void) {
         DeviceCtx& c = g_ctx[d];
         if (!c.ready) continue;
         cudaSetDevice(d);
-        c.ws.release(); c.stage_in.release(); c.stage_out.release(); for (int a2 = 0; a2 < 2; ++a2) for (int rg = 0; rg < 3; ++rg) c.chee_tables[a2][rg].release();
+        c.ws.release(); c.stage_in.release(); c.stage_out.release(); c.dec_tables.release(); for (int a2 = 0; a2 < 2; ++a2) for (int rg = 0; rg < 3; ++rg) c.chee_tables[a2][rg].release();
         c.chee_epoch = 0;
         if (c.d_size) cudaFree(c.d_size);
         if (c.h_size) cudaFreeHost(c.h_size);

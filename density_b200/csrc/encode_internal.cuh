@@ -40,9 +40,16 @@ cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, ui
                                  cudaStream_t stream, uint64_t* launches);
 
 // chameleon_decode.cu
-size_t cham_decode_workspace_bytes(size_t nbytes, int nruns_max);
+size_t cham_decode_workspace_bytes(size_t nbytes, size_t cap, int nruns_max);
 cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, int num_sms,
                                  uint64_t* d_out_size, uint32_t* d_nonquiet, cudaStream_t stream, uint64_t* launches);
+
+// cl_decode.cu (run-parallel Cheetah decode)
+size_t chee_decode_workspace_bytes(size_t nbytes, size_t cap, int num_sms);
+size_t chee_decode_tables_bytes(size_t nbytes, int num_sms);
+cudaError_t chee_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, uint8_t* tables, uint8_t* tail_ws,
+                                 int num_sms, uint64_t* d_out_size, uint32_t* d_fallback, cudaStream_t stream, uint64_t* launches);
+const void* chee_decode_status_ptr(uint8_t* ws, size_t nbytes, size_t cap, int num_sms, const void** cl_status);
 
 // scalar_codec.cu (Cheetah / Lion, in-order)
 size_t scalar_workspace_bytes(int alg);
@@ -50,6 +57,11 @@ cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* 
                           uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if_zero = nullptr);
 cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
                           uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if = nullptr);
+// tail loop only (codec.rs:102-123), continuing from the state the parallel decoder left: tables already in `ws`, boundary status
+// (bounds::DecStatus: tail offset, block count, protection state) and the last hash (cheedec::ClStatus::final_ctx) on the device;
+// runs only if *d_skip_if == 0
+cudaError_t scalar_decode_tail(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, const void* d_bounds_status,
+                               const void* d_cl_status, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_skip_if);
 
 // table helpers (sharded API, pipelined host path)
 cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches);

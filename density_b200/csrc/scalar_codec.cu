@@ -176,16 +176,13 @@ struct Dec {
     }
 };
 
+// main loop (codec.rs:88-100) and tail loop (codec.rs:102-123) of Codec::decode
 template <int ALG>
-__global__ void decode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, Tables T,
-                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (run_if && *run_if == 0) return;   // the parallel decoder already produced the result
+__device__ __forceinline__ void decode_loops(Dec<ALG>& D, Protection& ps, bool with_main) {
     constexpr uint32_t B = ALG == ALG_CHAMELEON ? 256 : ALG == ALG_CHEETAH ? 128 : 64;
     constexpr uint32_t SB = ALG == ALG_LION ? 6 : 8;
     constexpr uint32_t UNIT = ALG == ALG_CHAMELEON ? 8 : 4;
-    Dec<ALG> D; D.T = T; D.in = in; D.n = n; D.out = out; D.cap = cap;
-    Protection ps; ps.init();
+    const uint8_t* in = D.in; uint8_t* out = D.out; const uint64_t cap = D.cap;
     auto read_sig = [&]() -> uint64_t {  // codec.rs:29-31, lion.rs:338-351
         uint64_t v = 0;
         if (D.remaining() < SB) { D.bad = true; return 0; }
@@ -199,7 +196,7 @@ __global__ void decode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_
         D.oidx += len; D.idx += len;
     };
     // main loop, codec.rs:88-100
-    while (!D.bad && !D.overflow && D.remaining() >= SB + B) {
+    while (with_main && !D.bad && !D.overflow && D.remaining() >= SB + B) {
         if (ps.revert_to_copy()) { copy_raw(B); ps.decay(); }
         else {
             const uint64_t mark = D.idx;
@@ -226,6 +223,41 @@ __global__ void decode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_
             ps.update(D.idx - mark >= B);
         }
     }
+}
+
+template <int ALG>
+__global__ void decode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, Tables T,
+                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (run_if && *run_if == 0) return;   // the parallel decoder already produced the result
+    Dec<ALG> D; D.T = T; D.in = in; D.n = n; D.out = out; D.cap = cap;
+    Protection ps; ps.init();
+    decode_loops<ALG>(D, ps, true);
+    uint64_t res = D.oidx;
+    if (D.bad) { status->error = 3; res = 0; }
+    else if (D.overflow) { status->error = 2; res = 0; }
+    status->out_bytes = res;
+    if (d_out_size) *d_out_size = res;
+}
+
+// the boundary status block of decode_bounds.cuh and the iteration status of cl_decode.cu, as far as the tail needs them
+struct TailBounds { unsigned long long out_bytes, main_blocks, tail_off; unsigned int nonquiet, error, last_main_inc, seq, ps_penalty, ps_start, ps_prev, pad; };
+struct TailIter { unsigned int changed, unknown, done, rounds, final_ctx, gave_up, pad0, pad1; };
+
+// Tail loop only, continuing where the parallel main loop stopped (tables = what the folds left in the workspace).
+template <int ALG>
+__global__ void decode_tail_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, Tables T,
+                                   Status* __restrict__ status, const TailBounds* __restrict__ tb, const TailIter* __restrict__ ti,
+                                   uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ skip_if) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (skip_if && *skip_if != 0) return;   // the parallel decoder gave up: the in-order kernel (queued behind) does everything
+    constexpr uint32_t B = ALG == ALG_CHAMELEON ? 256 : ALG == ALG_CHEETAH ? 128 : 64;
+    Dec<ALG> D; D.T = T; D.in = in; D.n = n; D.out = out; D.cap = cap;
+    D.idx = tb->tail_off; D.oidx = tb->main_blocks * B; D.last_hash = ti->final_ctx;
+    Protection ps; ps.init();
+    ps.counter = tb->main_blocks; ps.previous_incompressible = tb->last_main_inc;   // quiet main loop: penalty 0, start 1
+    if (tb->seq) { ps.copy_penalty = tb->ps_penalty; ps.copy_penalty_start = tb->ps_start; ps.previous_incompressible = tb->ps_prev; }
+    decode_loops<ALG>(D, ps, false);
     uint64_t res = D.oidx;
     if (D.bad) { status->error = 3; res = 0; }
     else if (D.overflow) { status->error = 2; res = 0; }
@@ -276,6 +308,17 @@ cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* 
     case ALG_CHEETAH:   scalar::decode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
     default:            scalar::decode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
     }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t scalar_decode_tail(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, const void* d_bounds_status,
+                               const void* d_cl_status, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_skip_if) {
+    if (alg != ALG_CHEETAH) return cudaErrorInvalidValue;
+    scalar::Tables T = carve(alg, ws);   // the folds of cl_decode.cu have filled chunk_a / chunk_b / pred
+    Status* st = reinterpret_cast<Status*>(ws);
+    scalar::decode_tail_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, reinterpret_cast<const scalar::TailBounds*>(d_bounds_status),
+                                                                  reinterpret_cast<const scalar::TailIter*>(d_cl_status), d_out_size, d_skip_if);
     ++*launches;
     return cudaGetLastError();
 }

@@ -48,9 +48,21 @@ def test_scheme_reproduces_the_input(model, alg, kind, nbytes, nruns):
     assert n == data.size and (got == data).all(), (alg, kind, nruns)
 
 
-@pytest.mark.parametrize("alg", ["cheetah", "lion"])
-def test_rounds_stay_small_on_text(model, alg, dickens200k):
+def test_cheetah_rounds_stay_small_on_text(model, dickens200k):
+    """Cheetah: the prediction table is overwritten by 92 % of the quads (their hashes are in the stream), so a wrong context dies out
+    within a few quads and the rounds do not grow with the run count."""
     for nruns in (4, 16, 64, 256):
-        n, got, rounds, conv = run_model(model, alg, dickens200k, nruns)
+        n, got, rounds, conv = run_model(model, "cheetah", dickens200k, nruns)
         assert conv == 1 and n == dickens200k.size and (got == dickens200k).all()
-        assert rounds <= 12, (alg, nruns, rounds)
+        assert rounds <= 12, (nruns, rounds)
+
+
+def test_lion_rounds_grow_with_the_run_count(model):
+    """Lion (documented negative result): a misplaced operation desynchronises a whole 5-deep move-to-front list, wrong reads
+    keep producing wrong contexts, and exactness advances one run per round — still exact, but no better than in order. This is why
+    lion_decode stays on the in-order kernel."""
+    from density_b200 import synth
+    data = synth.synth_text(2 << 20).numpy()
+    n, got, rounds, conv = run_model(model, "lion", data, 16, max_rounds=64)
+    assert conv == 1 and n == data.size and (got == data).all()
+    assert rounds >= 8, rounds

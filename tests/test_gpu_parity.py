@@ -519,3 +519,55 @@ def test_lion_full_size_4gib_mixed_bit_exact(torch_cuda, codecs):
     got = d_out[:m].cpu().numpy()
     for off in range(0, m, 1 << 28):                                      # compare in pieces: bounded temporaries
         assert (got[off:off + (1 << 28)] == want[off:off + (1 << 28)]).all(), off
+
+
+@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("kind,nbytes", [("text", 5), ("text", 135), ("text", 136), ("text", 137), ("text", 300), ("text", 4096 + 3), ("text", 70001),
+                                         ("text", (1 << 20) + 5), ("text", 6 * (1 << 20) + 2), ("mixed", 3 * (1 << 20) + 1), ("random", 1 << 20),
+                                         ("zeros", (1 << 20) + 7), ("low", 500000), ("dickens", 200000), ("text", 33 * (1 << 20) + 66),
+                                         ("smixed", 40 * (1 << 20) + 3)])
+def test_cheetah_decode_parallel_paths(torch_cuda, codecs, path, kind, nbytes):
+    """Cheetah decode (cheetah.rs:67-103,152-185 through codec.rs:82-126) of oracle-made streams: path 1 = the run-parallel decoder
+    only (boundaries, unpack, symbolic chunk-map pass + fold, context rounds, in-order tail; no in-order fallback), path 0 = the same
+    with the in-order kernel queued behind as a safety net."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    if kind == "dickens":
+        data = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "dickens_200k.bin"), np.uint8)[:nbytes]
+    elif kind == "text":
+        data = synth.synth_text(nbytes).numpy()
+    elif kind == "smixed":
+        data = synth.synth_mixed(nbytes).numpy()
+    else:
+        data = payload(kind, nbytes, 7)
+    enc = oracle.encode("cheetah", data)
+    d_enc = torch.from_numpy(enc.copy()).cuda()
+    d_out = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.decode_device("cheetah", d_enc, enc.size, d_out[:nbytes], d_sz, path=path)
+    torch.cuda.synchronize()
+    assert int(d_sz.item()) == nbytes
+    assert (d_out[:nbytes].cpu().numpy() == data).all()
+    assert int(d_out[nbytes:].sum().item()) == 0, "wrote past the output capacity"
+
+
+def test_cheetah_round_trip_1gib_text_parallel_decoder(torch_cuda, codecs):
+    """BASELINE.json configs[2] (decode half) at full size: the run-parallel decoder alone (path 1) turns the 1 GiB stream back into
+    the input, on the device."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    n = 1 << 30
+    d_in = synth.synth_text(n, device="cuda")
+    d_enc = torch.zeros(codecs["cheetah"].safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    density_b200.encode_device("cheetah", d_in, d_enc, d_sz, path=1)
+    torch.cuda.synchronize()
+    m = int(d_sz.item())
+    assert m > 0
+    d_dec = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    density_b200.decode_device("cheetah", d_enc, m, d_dec, d_sz, path=1)
+    torch.cuda.synchronize()
+    assert int(d_sz.item()) == n
+    assert torch.equal(d_dec, d_in)

@@ -23,6 +23,12 @@ _SIGS = {
     "density_b200_shard_destroy": (None, [ctypes.c_void_p]),
     "density_b200_shard_phase1": (ctypes.c_int, [ctypes.c_void_p, _c_u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "density_b200_shard_phase2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "density_b200_sharded_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "density_b200_sharded_create": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "density_b200_sharded_destroy": (None, [ctypes.c_void_p]),
+    "density_b200_encode_sharded": (ctypes.c_int, [ctypes.c_void_p, _c_u8p, ctypes.c_size_t, _c_u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_int, _c_u8p, ctypes.c_size_t, ctypes.c_void_p]),
+    "density_b200_sharded_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "density_b200_table_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "density_b200_table_fold": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "density_b200_profile_enable": (None, [ctypes.c_int]),
@@ -32,6 +38,7 @@ _SIGS = {
     "density_b200_last_encode_was_fast": (ctypes.c_int, []),
     "density_b200_decode_status": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
     "density_b200_encode_status": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
+    "density_b200_test_set_stage_rounds": (None, [ctypes.c_int]),
     "density_b200_shutdown": (None, []),
     "density_b200_version": (ctypes.c_char_p, []),
 }

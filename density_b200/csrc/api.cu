@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "encode_internal.cuh"
 
+#include <dlfcn.h>
+
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -32,13 +34,15 @@ static void set_error(const char* what) { g_last_error = what; }
 // grow-only device buffer
 struct DevBuf {
     uint8_t* p = nullptr; size_t bytes = 0;
-    cudaError_t ensure(size_t need) {
+    // `stream`: the stream the buffer is about to be used on. The zero fill (the Cheetah / Lion encoder tables rely on starting out
+    // zeroed) is ordered on it; cudaFree of the old buffer synchronises the device, so nothing can still be using it.
+    cudaError_t ensure(size_t need, cudaStream_t stream = nullptr) {
         if (need <= bytes) return cudaSuccess;
         if (p) { cudaFree(p); p = nullptr; bytes = 0; }
         size_t want = need + need / 8 + 4096;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, need); want = need; }
-        if (e == cudaSuccess) { bytes = want; e = cudaMemset(p, 0, want); }   // the Cheetah run tables rely on starting out zeroed
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, need); want = need; }
+        if (e == cudaSuccess) { bytes = want; e = cudaMemsetAsync(p, 0, want, stream); }
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
@@ -63,6 +67,10 @@ struct DeviceCtx {
     static constexpr int PROF_RING = 64;
     cudaEvent_t ev[PROF_RING][4] = {};
     uint64_t prof_count = 0;           // encodes recorded since profile_enable(1)
+    // One workspace per device: a call may only start using it when the previous call (on whatever stream) has finished with it.
+    // Every enqueue ends with cudaEventRecord(ws_free, its stream) and starts with cudaStreamWaitEvent(its stream, ws_free).
+    cudaEvent_t ws_free = nullptr;
+    bool ws_free_recorded = false;
     std::mutex mu;
 };
 
@@ -93,6 +101,8 @@ static DeviceCtx* current_ctx() {
         e = cudaMallocHost(&c->h_size, 64);
         if (e == cudaSuccess) e = cudaMallocHost(&c->h_sizes, sizeof(uint64_t) * 4096);
         if (e != cudaSuccess) { set_error("cudaMallocHost", e); return nullptr; }
+        e = cudaEventCreateWithFlags(&c->ws_free, cudaEventDisableTiming);
+        if (e != cudaSuccess) { set_error("cudaEventCreate", e); return nullptr; }
         c->ready = true;
     }
     return c;
@@ -113,15 +123,34 @@ static bool is_device_pointer(const void* p) {
 // path: 0 auto (fast path with exact fallback), 1 fast only (no fallback), 2 protected walk only, 3 scalar kernel
 // path 4 (internal): Chameleon auto path for callers that may block on the stream (the synchronous reference-facing entry points): the
 // copy-map iteration gets up to 12 more batches of 8 rounds before the in-order walk may take over
+static bool ws_acquire(DeviceCtx* c, cudaStream_t stream) {
+    if (!c->ws_free_recorded) return true;
+    cudaError_t e = cudaStreamWaitEvent(stream, c->ws_free, 0);
+    if (e != cudaSuccess) { set_error("cudaStreamWaitEvent", e); return false; }
+    return true;
+}
+static void ws_release(DeviceCtx* c, cudaStream_t stream) {
+    if (cudaEventRecord(c->ws_free, stream) == cudaSuccess) c->ws_free_recorded = true;
+}
+
+static int encode_device_locked_impl(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                     uint64_t* d_out_size, cudaStream_t stream, int path);
 static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                 uint64_t* d_out_size, cudaStream_t stream, int path) {
+    if (!ws_acquire(c, stream)) return DENSITY_B200_ECUDA;
+    const int rc = encode_device_locked_impl(c, alg, d_in, n, d_out, cap, d_out_size, stream, path);
+    ws_release(c, stream);
+    return rc;
+}
+static int encode_device_locked_impl(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                     uint64_t* d_out_size, cudaStream_t stream, int path) {
     uint64_t launches = 0;
     cudaError_t e;
-    if (alg == ALG_CHAMELEON && path != 3) {
-        if ((reinterpret_cast<uintptr_t>(d_in) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 1)) { set_error("encode_device: d_in must be 4-byte and d_out 2-byte aligned"); return DENSITY_B200_EARG; }
+    const bool aligned = !(reinterpret_cast<uintptr_t>(d_in) & 3) && !(reinterpret_cast<uintptr_t>(d_out) & 1);
+    if (alg == ALG_CHAMELEON && path != 3 && aligned) {
         ChamLayout L;
         size_t need = cham_workspace_bytes(n, c->num_sms, &L);
-        e = c->ws.ensure(need);
+        e = c->ws.ensure(need, stream);
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
         c->layout = L;
         if (path == 2) {
@@ -144,10 +173,10 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
     } else if ((alg == ALG_CHEETAH || alg == ALG_LION) && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 3) && !(reinterpret_cast<uintptr_t>(d_out) & 1)) {
         // run-parallel Cheetah / Lion encoder; the exact in-order kernel is queued behind it and only runs if the copy map did not settle
         const size_t pw = (chee_workspace_bytes(n, c->num_sms) + 255) & ~(size_t)255;
-        e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg));
+        e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg), stream);
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
         DevBuf* tb = c->chee_tables[alg == ALG_LION];
-        for (int rg = 0; rg < 3 && e == cudaSuccess; ++rg) e = tb[rg].ensure(chee_tables_bytes(alg, rg, n, c->num_sms) + 256);
+        for (int rg = 0; rg < 3 && e == cudaSuccess; ++rg) e = tb[rg].ensure(chee_tables_bytes(alg, rg, n, c->num_sms) + 256, stream);
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
         if (c->chee_epoch > 0x0FFFFF00u) {                 // epochs exhausted (2^23 calls): start over on cleared tables
             for (int a2 = 0; a2 < 2; ++a2) for (int rg = 0; rg < 3; ++rg)
@@ -175,7 +204,7 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
         c->last_was_chameleon_fastpath_capable = 0;
     } else {
         if (reinterpret_cast<uintptr_t>(d_out) & 1) { set_error("encode_device: d_out must be 2-byte aligned"); return DENSITY_B200_EARG; }
-        e = c->ws.ensure(scalar_workspace_bytes(alg));
+        e = c->ws.ensure(scalar_workspace_bytes(alg), stream);
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
         e = scalar_encode(alg, d_in, n, d_out, cap, c->ws.p, d_out_size, stream, &launches);
         c->last_was_chameleon_fastpath_capable = 0;
@@ -186,15 +215,24 @@ static int encode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
 }
 
 // path: 0 auto (parallel decoder with exact in-order fallback), 1 parallel only, 3 in-order kernel only
+static int decode_device_locked_impl(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                     uint64_t* d_out_size, cudaStream_t stream, int path);
 static int decode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
                                 uint64_t* d_out_size, cudaStream_t stream, int path = 0) {
+    if (!ws_acquire(c, stream)) return DENSITY_B200_ECUDA;
+    const int rc = decode_device_locked_impl(c, alg, d_in, n, d_out, cap, d_out_size, stream, path);
+    ws_release(c, stream);
+    return rc;
+}
+static int decode_device_locked_impl(DeviceCtx* c, int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,
+                                     uint64_t* d_out_size, cudaStream_t stream, int path) {
     uint64_t launches = 0;
     cudaError_t e;
     const bool parallel_ok = alg == ALG_CHAMELEON && path != 3 && !(reinterpret_cast<uintptr_t>(d_in) & 1) && !(reinterpret_cast<uintptr_t>(d_out) & 3);
     if (parallel_ok) {
         // parallel decoder; the exact in-order kernel is queued behind it and only runs when the stream has copy-mode blocks
         const size_t pw = (cham_decode_workspace_bytes(n, cap, c->num_sms) + 255) & ~(size_t)255;
-        e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg));
+        e = c->ws.ensure(pw + 256 + scalar_workspace_bytes(alg), stream);
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
         uint32_t* d_nonquiet = reinterpret_cast<uint32_t*>(c->ws.p + pw);
         e = cham_decode_parallel(d_in, n, d_out, cap, c->ws.p, c->num_sms, d_out_size, d_nonquiet, stream, &launches);
@@ -208,8 +246,8 @@ static int decode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
         // run-parallel Cheetah decoder (cl_decode.cu) + in-order tail; the exact in-order kernel is queued behind it and only runs if
         // the context iteration did not settle within its round budget
         const size_t pw = (chee_decode_workspace_bytes(n, cap, c->num_sms) + 255) & ~(size_t)255;
-        e = c->ws.ensure(pw + 256 + 2 * ((scalar_workspace_bytes(alg) + 255) & ~(size_t)255));
-        if (e == cudaSuccess) e = c->dec_tables.ensure(chee_decode_tables_bytes(n, c->num_sms) + 256);
+        e = c->ws.ensure(pw + 256 + 2 * ((scalar_workspace_bytes(alg) + 255) & ~(size_t)255), stream);
+        if (e == cudaSuccess) e = c->dec_tables.ensure(chee_decode_tables_bytes(n, c->num_sms) + 256, stream);
         if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
         uint32_t* d_fallback = reinterpret_cast<uint32_t*>(c->ws.p + pw);
         uint8_t* tail_ws = c->ws.p + pw + 256;
@@ -227,7 +265,7 @@ static int decode_device_locked(DeviceCtx* c, int alg, const uint8_t* d_in, size
         if (e != cudaSuccess) { set_error("decode launch", e); return DENSITY_B200_ECUDA; }
         return DENSITY_B200_OK;
     }
-    e = c->ws.ensure(scalar_workspace_bytes(alg));
+    e = c->ws.ensure(scalar_workspace_bytes(alg), stream);
     if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
     e = scalar_decode(alg, d_in, n, d_out, cap, c->ws.p, d_out_size, stream, &launches);
     g_launches += launches;
@@ -314,6 +352,11 @@ static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_
     std::lock_guard<std::mutex> lk(c->mu);
     const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
     cudaError_t e;
+    if (in_dev || out_dev) {
+        // the call is synchronous and cannot know which stream produced a device buffer: wait for all of them
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("cudaDeviceSynchronize", e); return 0; }
+    }
     const uint8_t* d_in = in;
     uint8_t* d_out = out;
     size_t d_cap = out_cap;
@@ -484,6 +527,191 @@ int density_b200_shard_phase2(density_b200_shard* s, const uint32_t* d_carry_in,
     if (e != cudaSuccess) { set_error("shard phase2", e); return DENSITY_B200_ECUDA; }
     return DENSITY_B200_OK;
 }
+
+// ---- sharded Chameleon encode across the GPUs of one box: one process per GPU, NCCL over NVLink ---------------------
+// NCCL is resolved at run time from the library that is already in the process (torch loads its bundled libnccl.so.2), else the
+// system one: no link-time dependency, one NCCL per process.
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+struct nccl_unique_id { char internal[128]; };
+enum { NCCL_UINT8 = 1, NCCL_UINT32 = 3 };
+struct NcclApi {
+    int (*GetUniqueId)(nccl_unique_id*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        auto sym = [&](const char* n) { return dlsym(h, n); };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+        api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+    });
+    return api.ok ? &api : nullptr;
+}
+bool nccl_check(int rc, const char* what) {
+    if (rc == 0) return true;
+    NcclApi* a = nccl_api();
+    std::string m = std::string(what) + ": " + ((a && a->GetErrorString) ? a->GetErrorString(rc) : "NCCL error");
+    dns::set_error(m.c_str());
+    return false;
+}
+}  // namespace
+
+struct density_b200_sharded {
+    int rank = 0, world = 1, num_sms = 0;
+    nccl_comm_t comm = nullptr;
+    DevBuf ws, aux;                 // aux: gathered tables [world][65536] + carry [65536] + seam words [world][8] + offsets [world + 1] + size
+    ChamLayout L{};
+    uint64_t* h_offsets = nullptr;  // pinned, world + 1
+    cudaEvent_t ev[6] = {};         // stage timing of the last call: start, flag pass, exchange, phase 2 up to emit, emit, gather
+    bool timed = false;
+};
+
+int density_b200_sharded_unique_id(uint8_t* out128) {
+    g_last_error.clear();
+    NcclApi* a = nccl_api();
+    if (!a || !out128) { set_error("NCCL is not available in this process"); return DENSITY_B200_ECUDA; }
+    nccl_unique_id id;
+    if (!nccl_check(a->GetUniqueId(&id), "ncclGetUniqueId")) return DENSITY_B200_ECUDA;
+    memcpy(out128, id.internal, 128);
+    return DENSITY_B200_OK;
+}
+
+density_b200_sharded* density_b200_sharded_create(const uint8_t* nccl_unique_id_128, int rank, int world) {
+    g_last_error.clear();
+    if (world < 1 || rank < 0 || rank >= world) { set_error("bad rank / world"); return nullptr; }
+    DeviceCtx* c = current_ctx();
+    if (!c) return nullptr;
+    density_b200_sharded* h = new density_b200_sharded();
+    h->rank = rank; h->world = world; h->num_sms = c->num_sms;
+    if (world > 1) {
+        NcclApi* a = nccl_api();
+        if (!a || !nccl_unique_id_128) { set_error("NCCL is not available / no unique id"); delete h; return nullptr; }
+        nccl_unique_id id; memcpy(id.internal, nccl_unique_id_128, 128);
+        if (!nccl_check(a->CommInitRank(&h->comm, world, id, rank), "ncclCommInitRank")) { delete h; return nullptr; }
+    }
+    if (cudaMallocHost(&h->h_offsets, sizeof(uint64_t) * (world + 2)) != cudaSuccess) { set_error("cudaMallocHost"); delete h; return nullptr; }
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    return h;
+}
+
+void density_b200_sharded_destroy(density_b200_sharded* h) {
+    if (!h) return;
+    if (h->comm) { NcclApi* a = nccl_api(); if (a) a->CommDestroy(h->comm); }
+    h->ws.release(); h->aux.release();
+    if (h->h_offsets) cudaFreeHost(h->h_offsets);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    delete h;
+}
+
+// One bit-exact stream cut across `world` GPUs; this rank's shard is d_in[0 .. n) (n % 256 == 0 except on the last rank).
+// All work is enqueued on `stream`. With gather_root >= 0 the call BLOCKS on the stream once (the piece sizes must reach the host before
+// the variable-length ncclSend / ncclRecv can be posted) and the pieces land in d_gather on rank gather_root at their stream offsets.
+int density_b200_encode_sharded(density_b200_sharded* h, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                                uint32_t* d_flags, uint64_t* d_total_size, int gather_root, uint8_t* d_gather, size_t gather_cap, void* stream_v) {
+    g_last_error.clear();
+    if (!h || (!d_in && n) || !d_out || !d_out_size) { set_error("null pointer"); return DENSITY_B200_EARG; }
+    const bool last = h->rank == h->world - 1;
+    if (!last && (n % 256)) { set_error("non-final shards must be a multiple of 256 bytes"); return DENSITY_B200_EARG; }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 1)) { set_error("d_in must be 4-byte, d_out 2-byte aligned"); return DENSITY_B200_EARG; }
+    if (gather_root >= h->world) { set_error("bad gather root"); return DENSITY_B200_EARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+    NcclApi* a = h->world > 1 ? nccl_api() : nullptr;
+    const size_t W = (size_t)h->world;
+    const size_t aux_tables = W * 65536 * sizeof(uint32_t), aux_carry = 65536 * sizeof(uint32_t), aux_words = W * 8 * sizeof(uint32_t);
+    cudaError_t e = h->ws.ensure(cham_workspace_bytes(n, h->num_sms, &h->L), st);
+    if (e == cudaSuccess) e = h->aux.ensure(aux_tables + aux_carry + aux_words + (W + 2) * sizeof(uint64_t) + 256, st);
+    if (e != cudaSuccess) { set_error("workspace cudaMalloc", e); return DENSITY_B200_ECUDA; }
+    uint32_t* d_tables = reinterpret_cast<uint32_t*>(h->aux.p);
+    uint32_t* d_carry = reinterpret_cast<uint32_t*>(h->aux.p + aux_tables);
+    uint32_t* d_words = reinterpret_cast<uint32_t*>(h->aux.p + aux_tables + aux_carry);
+    uint64_t* d_offsets = reinterpret_cast<uint64_t*>(h->aux.p + aux_tables + aux_carry + aux_words);
+    const uint32_t nruns = cham_pick_runs(n, h->num_sms);
+    uint64_t launches = 0;
+    cudaEventRecord(h->ev[0], st);
+    // phase 1: flags with unknown carry-in; my last-writer table lands in my slot of the gather buffer
+    cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (n) e = cham_encode_phase1(d_in, n, h->ws.p, h->L, nruns, d_tables + (size_t)h->rank * 65536, st, &launches);
+    else e = cudaMemsetAsync(d_tables + (size_t)h->rank * 65536, 0, 65536 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) { set_error("sharded phase 1", e); return DENSITY_B200_ECUDA; }
+    cudaEventRecord(h->ev[1], st);
+    // the one exchange step of the path: 256 KiB per rank over NVLink, then ONE fold kernel
+    if (h->world > 1) {
+        if (!a) { set_error("NCCL is not available"); return DENSITY_B200_ECUDA; }
+        if (!nccl_check(a->AllGather(d_tables + (size_t)h->rank * 65536, d_tables, 65536, NCCL_UINT32, h->comm, st), "ncclAllGather(tables)")) return DENSITY_B200_ECUDA;
+    }
+    e = cham_rank_fold(d_tables, (uint32_t)h->rank, d_carry, st, &launches);
+    cudaEventRecord(h->ev[2], st);
+    // phase 2: carry-in, first-touch flags, sizes, scan, emit (seams are judged below, exactly, once every shard knows its flags)
+    pev[2] = h->ev[3]; pev[3] = h->ev[4];
+    if (e == cudaSuccess) e = cham_encode_phase2(d_in, n, h->ws.p, h->L, nruns, d_carry, d_out, cap, d_out_size, false, false, st, &launches, n ? pev : nullptr);
+    if (!n) { cudaEventRecord(h->ev[3], st); cudaEventRecord(h->ev[4], st); }
+    if (e == cudaSuccess && n) e = cham_seam_words(h->ws.p, h->L, n, d_out_size, d_words + 8 * h->rank, st, &launches);
+    else if (e == cudaSuccess) e = cudaMemsetAsync(d_words + 8 * h->rank, 0, 8 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) { set_error("sharded phase 2", e); return DENSITY_B200_ECUDA; }
+    if (h->world > 1 && !nccl_check(a->AllGather(d_words + 8 * h->rank, d_words, 8, NCCL_UINT32, h->comm, st), "ncclAllGather(seams)")) return DENSITY_B200_ECUDA;
+    e = cham_seam_verdict(d_words, (uint32_t)h->world, (uint32_t)h->rank, d_flags, d_total_size, d_offsets, st, &launches);
+    if (e != cudaSuccess) { set_error("seam verdict", e); return DENSITY_B200_ECUDA; }
+    if (gather_root >= 0) {
+        // variable-length gather of the pieces at their stream offsets: sizes -> host -> grouped send / recv
+        e = cudaMemcpyAsync(h->h_offsets, d_offsets, (W + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("gather: sizes to host", e); return DENSITY_B200_ECUDA; }
+        const uint64_t total = h->h_offsets[W];
+        const uint64_t my_off = h->h_offsets[h->rank], my_size = h->h_offsets[h->rank + 1] - my_off;
+        if (h->rank == gather_root) {
+            if (!d_gather || gather_cap < total) { set_error("gather buffer too small"); return DENSITY_B200_ECAPACITY; }
+            if (my_size) e = cudaMemcpyAsync(d_gather + my_off, d_out, my_size, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { set_error("gather: local piece", e); return DENSITY_B200_ECUDA; }
+        }
+        if (h->world > 1) {
+            if (!nccl_check(a->GroupStart(), "ncclGroupStart")) return DENSITY_B200_ECUDA;
+            bool ok = true;
+            if (h->rank == gather_root) {
+                for (int r = 0; r < h->world && ok; ++r) {
+                    const uint64_t sz = h->h_offsets[r + 1] - h->h_offsets[r];
+                    if (r != h->rank && sz) ok = nccl_check(a->Recv(d_gather + h->h_offsets[r], sz, NCCL_UINT8, r, h->comm, st), "ncclRecv");
+                }
+            } else if (my_size) ok = nccl_check(a->Send(d_out, my_size, NCCL_UINT8, gather_root, h->comm, st), "ncclSend");
+            if (!nccl_check(a->GroupEnd(), "ncclGroupEnd") || !ok) return DENSITY_B200_ECUDA;
+        }
+    }
+    cudaEventRecord(h->ev[5], st);
+    h->timed = true;
+    g_launches += launches;
+    return DENSITY_B200_OK;
+}
+
+/* stage times of the last density_b200_encode_sharded call (waits for it): out_ms[0] flag pass, [1] table exchange + fold,
+   [2] carry / resolve / sizes / scan, [3] emit, [4] seam exchange + gather. */
+int density_b200_sharded_profile(density_b200_sharded* h, float* out_ms) {
+    if (!h || !out_ms || !h->timed) return DENSITY_B200_EARG;
+    cudaError_t e = cudaEventSynchronize(h->ev[5]);
+    for (int k = 0; k < 5 && e == cudaSuccess; ++k) e = cudaEventElapsedTime(&out_ms[k], h->ev[k], h->ev[k + 1]);
+    if (e != cudaSuccess) { set_error("sharded_profile", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+
 int density_b200_table_init(uint32_t* d_table, void* stream) {
     uint64_t l = 0;
     cudaError_t e = cham_table_init(d_table, reinterpret_cast<cudaStream_t>(stream), &l);
@@ -541,6 +769,7 @@ int density_b200_last_encode_was_fast(void) {
     if (c->last_was_chameleon_fastpath_capable == 2) return 1;
     if (!c->last_was_chameleon_fastpath_capable || !c->ws.p) return 0;
     Status st;
+    if (cudaDeviceSynchronize() != cudaSuccess) return 0;
     if (cudaMemcpy(&st, c->ws.p + c->layout.status, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return st.nonquiet ? 0 : 1;
 }
@@ -569,6 +798,7 @@ void density_b200_shutdown(void) {
         if (c.d_size) cudaFree(c.d_size);
         if (c.h_size) cudaFreeHost(c.h_size);
         if (c.stream) cudaStreamDestroy(c.stream);
+        if (c.ws_free) { cudaEventDestroy(c.ws_free); c.ws_free = nullptr; c.ws_free_recorded = false; }
         if (c.h2d_stream) cudaStreamDestroy(c.h2d_stream);
         if (c.d2h_stream) cudaStreamDestroy(c.d2h_stream);
         if (c.h_sizes) cudaFreeHost(c.h_sizes);
@@ -578,6 +808,9 @@ void density_b200_shutdown(void) {
     }
     if (cur >= 0) cudaSetDevice(cur);
 }
+
+/* test hook: rounds per stage of the Cheetah / Lion copy-map iteration (1..7; 7 = default) */
+void density_b200_test_set_stage_rounds(int k) { g_chee_stage_rounds = (k >= 1 && k <= 7) ? k : 7; }
 
 const char* density_b200_version(void) { return "density_b200 0.1.0 (sm_100a)"; }
 

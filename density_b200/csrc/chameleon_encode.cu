@@ -951,6 +951,46 @@ __global__ void cham_table_fold_k(uint32_t* __restrict__ acc, const uint32_t* __
     if (i < 65536) { uint32_t v = next[i]; if (v & 0x10000u) acc[i] = v; }
 }
 
+// carry-in dictionary of shard `rank` = left fold of the last-writer tables of the shards before it over the stream-start state
+// (one kernel for the whole fold; `tables` = [world][65536] as gathered over NVLink)
+__global__ void cham_rank_fold_k(const uint32_t* __restrict__ tables, uint32_t rank, uint32_t* __restrict__ carry) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536) return;
+    uint32_t c = (i == 0) ? 0x10000u : 0u;            // stream start: bucket 0 "holds quad 0" (chameleon.rs:41,89-91)
+    for (uint32_t r = 0; r < rank; ++r) { const uint32_t v = tables[(size_t)r * 65536 + i]; if (v & 0x10000u) c = v; }
+    carry[i] = c;
+}
+// what a shard tells the others after its phase 2: {first block incompressible, last block incompressible, not quiet or error, 0, size}
+__global__ void cham_seam_words_k(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblocks, const Status* __restrict__ st,
+                                  const uint64_t* __restrict__ d_out_size, uint32_t* __restrict__ words /* 8 x u32 */) {
+    if (threadIdx.x || blockIdx.x) return;
+    auto inc = [&](uint64_t b) { return (nbytes - b * 256 >= 256) && (__popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]) <= 4); };
+    words[0] = nblocks ? (inc(0) ? 1u : 0u) : 0u;
+    words[1] = nblocks ? (inc(nblocks - 1) ? 1u : 0u) : 0u;
+    words[2] = (nblocks && (st->nonquiet || st->error)) ? 1u : 0u;
+    words[3] = nblocks ? 1u : 0u;                        // the shard has blocks at all
+    const uint64_t sz = *d_out_size;
+    words[4] = (uint32_t)sz; words[5] = (uint32_t)(sz >> 32); words[6] = 0; words[7] = 0;
+}
+// all ranks evaluate the same thing: the stream is quiet iff every shard is and no seam joins two incompressible blocks
+// (protection_state.rs:38-43 across the cut); also the stream length and this rank's offset in it
+__global__ void cham_seam_verdict_k(const uint32_t* __restrict__ all_words, uint32_t world, uint32_t rank, uint32_t* __restrict__ d_flags,
+                                    uint64_t* __restrict__ d_total, uint64_t* __restrict__ d_sizes /* world + 1: offsets */) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t bad = 0, prev_inc = 0; uint64_t off = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+        const uint32_t* w = all_words + 8 * r;
+        if (w[2]) bad = 1;
+        if (w[3]) { if (prev_inc && w[0]) bad = 1; prev_inc = w[1]; }
+        if (d_sizes) d_sizes[r] = off;
+        off += (uint64_t)w[4] | ((uint64_t)w[5] << 32);
+    }
+    if (d_sizes) d_sizes[world] = off;
+    if (d_flags) *d_flags = bad;
+    if (d_total) *d_total = off;
+    (void)rank;
+}
+
 }  // namespace cham
 
 // ------------------------------------------------------------------------------------------------------
@@ -1196,6 +1236,23 @@ cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint3
                               uint32_t ngroups, Status* st, uint64_t cap, uint64_t* d_out_size, cudaStream_t stream) {
     scan_groups_local<<<ngroups, SCAN_T, 0, stream>>>(tile_bytes, ntiles, tile_local, group_total);
     scan_group_totals<<<1, SCAN_T, 0, stream>>>(group_total, ngroups, group_off, st, cap, d_out_size);
+    return cudaGetLastError();
+}
+cudaError_t cham_rank_fold(const uint32_t* d_tables, uint32_t rank, uint32_t* d_carry, cudaStream_t stream, uint64_t* launches) {
+    cham_rank_fold_k<<<65536 / 256, 256, 0, stream>>>(d_tables, rank, d_carry);
+    ++*launches;
+    return cudaGetLastError();
+}
+cudaError_t cham_seam_words(const uint8_t* ws, const ChamLayout& L, size_t nbytes, const uint64_t* d_out_size, uint32_t* d_words, cudaStream_t stream, uint64_t* launches) {
+    cham_seam_words_k<<<1, 1, 0, stream>>>(reinterpret_cast<const uint32_t*>(ws + L.sigw), nbytes, (nbytes + 255) / 256,
+                                           reinterpret_cast<const Status*>(ws + L.status), d_out_size, d_words);
+    ++*launches;
+    return cudaGetLastError();
+}
+cudaError_t cham_seam_verdict(const uint32_t* d_all_words, uint32_t world, uint32_t rank, uint32_t* d_flags, uint64_t* d_total, uint64_t* d_offsets,
+                              cudaStream_t stream, uint64_t* launches) {
+    cham_seam_verdict_k<<<1, 1, 0, stream>>>(d_all_words, world, rank, d_flags, d_total, d_offsets);
+    ++*launches;
     return cudaGetLastError();
 }
 cudaError_t cham_table_init(uint32_t* d_table, cudaStream_t stream, uint64_t* launches) {

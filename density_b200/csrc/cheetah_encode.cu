@@ -627,6 +627,8 @@ __global__ void chee_chain_gate(Status* __restrict__ st, const Status* __restric
 
 using namespace chee;
 
+int g_chee_stage_rounds = 7;   // rounds per stage of the copy-map iteration (7 = all; tests lower it, see density_b200_test_set_stage_rounds)
+
 struct CheeLayout {
     size_t status, Pbits, Abits, Bbits, F0, F1, F2, copymap, copymap2, incb, seg_state, ctx0, tile_bytes, tile_local, group_total, group_off, total;
 };
@@ -741,9 +743,8 @@ cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, ui
     };
 
     // A stage = up to 8 rounds on one Status block (prot_iterate owns 8 grid-barrier slots per block).
-    // test hook: DENSITY_B200_CHEE_ROUNDS=k (1..7) cuts every stage to rounds first..k so that the resume path can be exercised
-    int last_it = 7;
-    if (const char* v = getenv("DENSITY_B200_CHEE_ROUNDS")) { const int k = atoi(v); if (k >= 1 && k <= 7) last_it = k; }
+    // test hook (density_b200_test_set_stage_rounds): cut every stage to rounds first..k so that the resume path can be exercised
+    const int last_it = g_chee_stage_rounds;
     auto stage = [&](Status* st, const Status* inherit, int first_it, size_t nb, uint32_t runs, uint32_t ep0) -> cudaError_t {
         chee_chain_gate<<<1, 1, 0, stream>>>(st, inherit); ++*launches;
         for (int it = first_it; it <= last_it; ++it) {

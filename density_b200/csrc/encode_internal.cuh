@@ -33,6 +33,7 @@ cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint3
                               uint32_t ngroups, Status* st, uint64_t cap, uint64_t* d_out_size, cudaStream_t stream);
 
 // cheetah_encode.cu
+extern int g_chee_stage_rounds;
 size_t chee_workspace_bytes(size_t nbytes, int num_sms);
 size_t chee_tables_bytes(int alg, int region, size_t nbytes, int num_sms);
 cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws, uint8_t* const tables[3],
@@ -66,6 +67,10 @@ cudaError_t scalar_decode_tail(int alg, const uint8_t* d_in, size_t nbytes, uint
 // table helpers (sharded API, pipelined host path)
 cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches);
 cudaError_t cham_table_init(uint32_t* d_table, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_rank_fold(const uint32_t* d_tables, uint32_t rank, uint32_t* d_carry, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_seam_words(const uint8_t* ws, const ChamLayout& L, size_t nbytes, const uint64_t* d_out_size, uint32_t* d_words, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_seam_verdict(const uint32_t* d_all_words, uint32_t world, uint32_t rank, uint32_t* d_flags, uint64_t* d_total, uint64_t* d_offsets,
+                              cudaStream_t stream, uint64_t* launches);
 cudaError_t cham_table_fold(uint32_t* d_acc, const uint32_t* d_next, cudaStream_t stream, uint64_t* launches);
 
 }  // namespace dns

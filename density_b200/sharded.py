@@ -84,3 +84,61 @@ class ShardedChameleonEncoder:
                                                  d_flags.data_ptr(), stream)
         if rc:
             raise _lib.DensityB200Error(f"shard_phase2 rc={rc}: {_lib.last_error()}")
+
+
+class ShardedEncoder:
+    """The C++ multi-GPU path (`density_b200_encode_sharded`, include/density_b200.h): one process per GPU; the library owns its NCCL
+    communicator (the 128-byte id travels once through torch.distributed), the table all-gather, the single fold kernel, the exact
+    seam verdict and the optional variable-length gather of the pieces to one rank. torch.distributed is only used to hand out the id.
+    """
+
+    def __init__(self, device, group=None):
+        self._lib = _lib.load()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                buf = (ctypes.c_uint8 * 128)()
+                rc = self._lib.density_b200_sharded_unique_id(buf)
+                if rc:
+                    raise _lib.DensityB200Error(f"sharded_unique_id rc={rc}: {_lib.last_error()}")
+                ident = torch.tensor(list(buf), dtype=torch.uint8)
+            t = ident.to(device) if dist.get_backend(group) == "nccl" else ident
+            dist.broadcast(t, src=0, group=group)
+            ident = t.cpu()
+        self._id = ident.contiguous()
+        self._h = self._lib.density_b200_sharded_create(self._id.data_ptr() if self.world > 1 else None, self.rank, self.world)
+        if not self._h:
+            raise _lib.DensityB200Error(_lib.last_error())
+        self.d_total = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.density_b200_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode(self, d_in, d_out, d_size, d_flags, gather_root=-1, d_gather=None):
+        """Enqueue on torch's current stream. d_size int64[1]: this rank's piece; d_flags int32[1]: != 0 -> the stream is not quiet and
+        the pieces are void; self.d_total int64[1]: stream length. gather_root >= 0: pieces gathered into d_gather on that rank (blocks)."""
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = self._lib.density_b200_encode_sharded(self._h, d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(), d_size.data_ptr(),
+                                                   d_flags.data_ptr(), self.d_total.data_ptr(), int(gather_root),
+                                                   d_gather.data_ptr() if d_gather is not None else None,
+                                                   d_gather.numel() if d_gather is not None else 0, stream)
+        if rc:
+            raise _lib.DensityB200Error(f"encode_sharded rc={rc}: {_lib.last_error()}")
+
+    def profile(self):
+        """stage times (ms) of the last call: flag pass, table exchange + fold, carry / resolve / sizes / scan, emit, seams + gather"""
+        out = (ctypes.c_float * 5)()
+        rc = self._lib.density_b200_sharded_profile(self._h, out)
+        if rc:
+            raise _lib.DensityB200Error(f"sharded_profile rc={rc}: {_lib.last_error()}")
+        return [float(x) for x in out]

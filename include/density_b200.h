@@ -129,6 +129,26 @@ DENSITY_B200_API int density_b200_shard_phase2(density_b200_shard*, const uint32
 DENSITY_B200_API int density_b200_table_init(uint32_t* d_table, void* stream);
 DENSITY_B200_API int density_b200_table_fold(uint32_t* d_acc, const uint32_t* d_next, void* stream);
 
+/*
+ * The same in C++ end to end (what bench.py --gpus N runs): one process per GPU, the exchange over NCCL (NVLink / NVSwitch).
+ *   density_b200_sharded_unique_id   rank 0 makes the 128-byte NCCL id; the caller hands it to every rank (e.g. torch.distributed broadcast)
+ *   density_b200_sharded_create      joins the communicator (world == 1: no NCCL needed, id may be NULL)
+ *   density_b200_encode_sharded      phase 1 -> ncclAllGather of the 256 KiB tables -> ONE fold kernel -> phase 2 -> seam verdict
+ *                                    (ncclAllGather of 32 bytes per rank: first / last block incompressible, quiet, size) -> optional
+ *                                    variable-length gather of the pieces to `gather_root` (grouped ncclSend / ncclRecv at prefix-sum
+ *                                    offsets). *d_flags != 0: the stream is not quiet (a copy-mode block somewhere, or two incompressible
+ *                                    blocks across a cut): the pieces are void and the caller encodes on one device instead.
+ *                                    *d_total_size = length of the whole stream, on every rank. gather_root < 0: no gather, nothing blocks.
+ */
+typedef struct density_b200_sharded density_b200_sharded; /* opaque */
+DENSITY_B200_API int density_b200_sharded_unique_id(uint8_t* out128);
+DENSITY_B200_API density_b200_sharded* density_b200_sharded_create(const uint8_t* nccl_unique_id_128, int rank, int world);
+DENSITY_B200_API void density_b200_sharded_destroy(density_b200_sharded*);
+DENSITY_B200_API int density_b200_encode_sharded(density_b200_sharded*, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap, uint64_t* d_out_size,
+                                uint32_t* d_flags, uint64_t* d_total_size, int gather_root, uint8_t* d_gather, size_t gather_cap, void* stream);
+/* stage times (ms) of the last call: [0] flag pass, [1] table exchange + fold, [2] carry / resolve / sizes / scan, [3] emit, [4] seams + gather */
+DENSITY_B200_API int density_b200_sharded_profile(density_b200_sharded*, float* out_ms5);
+
 /* ---- per-stage device timing of the last Chameleon encode on the current device ------- */
 /* When enabled, density_b200_encode_device records CUDA events on the caller's stream around the flag pass
    and the emit pass of every call (ring of 64 calls; enable(1) resets it). density_b200_profile_get waits
@@ -147,6 +167,9 @@ DENSITY_B200_API uint64_t density_b200_kernel_launches(void);
 DENSITY_B200_API int density_b200_last_encode_was_fast(void);
 /* Free all cached device workspaces. */
 DENSITY_B200_API void density_b200_shutdown(void);
+/* Test hook: cut every stage of the Cheetah / Lion copy-map iteration to k rounds (1..7, default 7) so that the host-resumed
+   iteration of path 4 can be exercised on ordinary inputs. */
+DENSITY_B200_API void density_b200_test_set_stage_rounds(int k);
 /* Library version string. */
 DENSITY_B200_API const char* density_b200_version(void);
 

@@ -256,7 +256,7 @@ def test_chameleon_encode_chained_copy_mode_episodes(torch_cuda, codecs):
 
 @pytest.mark.parametrize("alg", ["cheetah", "lion"])
 @pytest.mark.parametrize("nbytes", [33 * (1 << 20) + 66, (1 << 20) + 5])
-def test_cheetah_lion_blocking_iteration_resumes(torch_cuda, codecs, alg, nbytes, monkeypatch):
+def test_cheetah_lion_blocking_iteration_resumes(torch_cuda, codecs, alg, nbytes):
     """Path 4 (what the synchronous reference symbols use): when the copy map has not settled after the enqueued stages the host reads
     the verdict and resumes the iteration instead of leaving the stream to the in-order kernel. The test hook cuts every stage to one
     round so that the resume path is exercised on ordinary text; the in-order kernel would need seconds for the larger input."""
@@ -271,12 +271,15 @@ def test_cheetah_lion_blocking_iteration_resumes(torch_cuda, codecs, alg, nbytes
     d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
     density_b200.encode_device(alg, d_in, d_out, d_sz, path=4)          # warm (workspace allocation)
     torch.cuda.synchronize()
-    monkeypatch.setenv("DENSITY_B200_CHEE_ROUNDS", "1")
-    d_out.zero_(); d_sz.zero_()
-    t0 = time.perf_counter()
-    density_b200.encode_device(alg, d_in, d_out, d_sz, path=4)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    density_b200.load().density_b200_test_set_stage_rounds(1)
+    try:
+        d_out.zero_(); d_sz.zero_()
+        t0 = time.perf_counter()
+        density_b200.encode_device(alg, d_in, d_out, d_sz, path=4)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        density_b200.load().density_b200_test_set_stage_rounds(7)
     n = int(d_sz.item())
     assert n == want.size and (d_out[:n].cpu().numpy() == want).all()
     if nbytes > (1 << 25):
@@ -571,3 +574,85 @@ def test_cheetah_round_trip_1gib_text_parallel_decoder(torch_cuda, codecs):
     torch.cuda.synchronize()
     assert int(d_sz.item()) == n
     assert torch.equal(d_dec, d_in)
+
+
+def test_encode_sharded_cpp_entry_world1(torch_cuda, codecs):
+    """density_b200_encode_sharded (C++: phase 1 -> fold kernel -> phase 2 -> seam verdict -> gather) with one rank: the piece and the
+    gathered stream equal the oracle's; a non-quiet shard is reported, not emitted silently."""
+    torch = torch_cuda
+    from density_b200 import sharded, synth
+    n = 5 * (1 << 20) + 1021
+    data = synth.synth_text(n).numpy()
+    want = oracle.encode("chameleon", data)
+    enc = sharded.ShardedEncoder(torch.device("cuda"))
+    d_in = torch.from_numpy(data.copy()).cuda()
+    d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(n), dtype=torch.uint8, device="cuda")
+    d_gather = torch.zeros(d_out.numel(), dtype=torch.uint8, device="cuda")
+    d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_fl = torch.ones(1, dtype=torch.int32, device="cuda")
+    enc.encode(d_in, d_out, d_sz, d_fl, gather_root=0, d_gather=d_gather)
+    torch.cuda.synchronize()
+    assert int(d_fl.item()) == 0 and int(d_sz.item()) == want.size == int(enc.d_total.item())
+    assert (d_out[:want.size].cpu().numpy() == want).all() and (d_gather[:want.size].cpu().numpy() == want).all()
+    bad = payload("random", 1 << 20, 3)
+    d_in2 = torch.from_numpy(bad.copy()).cuda()
+    enc.encode(d_in2, d_out, d_sz, d_fl)
+    torch.cuda.synchronize()
+    assert int(d_fl.item()) != 0
+    enc.close()
+
+
+def _nccl_worker(rank, world, port, n_per_rank, q):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import density_b200
+    from density_b200 import sharded, synth
+    enc = sharded.ShardedEncoder(dev)
+    d_in = synth.synth_text(n_per_rank, device=dev, first_page=rank * (n_per_rank // synth.PAGE))
+    cap = density_b200.Chameleon.safe_encode_buffer_size(n_per_rank)
+    d_out = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    d_gather = torch.zeros(world * cap, dtype=torch.uint8, device=dev) if rank == 0 else None
+    d_sz = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_fl = torch.ones(1, dtype=torch.int32, device=dev)
+    enc.encode(d_in, d_out, d_sz, d_fl, gather_root=0, d_gather=d_gather)
+    torch.cuda.synchronize()
+    total = int(enc.d_total.item())
+    q.put((rank, int(d_fl.item()), d_out[:int(d_sz.item())].cpu().numpy(), total, d_gather[:total].cpu().numpy() if rank == 0 else None))
+    dist.barrier()
+    enc.close()
+    dist.destroy_process_group()
+
+
+def test_encode_sharded_two_ranks_nccl_equals_oracle(torch_cuda, codecs):
+    """Two processes, two GPUs, NCCL over NVLink: the concatenated pieces AND the stream gathered on rank 0 equal oracle.encode of the
+    whole buffer (codec.rs:72-80: one stream). Skipped on a single-GPU box (the driver's 2 / 4 / 8-GPU bench runs the same check)."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from density_b200 import synth
+    world, n_per = 2, 48 * (1 << 20)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, 29713, n_per, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, fl, piece, total, gathered = q.get(timeout=600)
+        got[r] = (fl, piece, total, gathered)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    whole = synth.synth_text(world * n_per).numpy()
+    want = oracle.encode("chameleon", whole)
+    assert all(got[r][0] == 0 for r in range(world))
+    cat = np.concatenate([got[r][1] for r in range(world)])
+    assert cat.size == want.size and (cat == want).all()
+    assert got[0][2] == want.size and (got[0][3] == want).all()

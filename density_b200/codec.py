@@ -131,6 +131,49 @@ class Lion(_Codec):
 CODECS = {"chameleon": Chameleon, "cheetah": Cheetah, "lion": Lion}
 
 
+class CodecInstance:
+    """A Codec instance that is reused across calls (`let mut c = Chameleon::new(); c.encode(a, ..); c.encode(b, ..)`,
+    codec.rs:16,72,82): the dictionary survives until clear_state(); the protection state is fresh in every call."""
+
+    def __init__(self, alg):
+        self.alg = alg
+        self._lib = _lib.load()
+        self._h = self._lib.density_b200_codec_create(ALG_IDS[alg])
+        if not self._h:
+            raise _lib.DensityB200Error(_lib.last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.density_b200_codec_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear_state(self):
+        if self._lib.density_b200_codec_clear_state(self._h):
+            raise _lib.DensityB200Error(_lib.last_error())
+
+    def encode(self, input, output):
+        ip, n, k1 = _ptr_len(input)
+        op, cap, k2 = _ptr_len(output, writable=True)
+        r = self._lib.density_b200_codec_encode(self._h, ip, n, op, cap)
+        if r == 0 and n != 0:
+            raise EncodeError(_lib.last_error() or "encode failed")
+        return r
+
+    def decode(self, input, output):
+        ip, n, k1 = _ptr_len(input)
+        op, cap, k2 = _ptr_len(output, writable=True)
+        r = self._lib.density_b200_codec_decode(self._h, ip, n, op, cap)
+        if r == 0 and n != 0:
+            raise DecodeError(_lib.last_error() or "decode failed")
+        return r
+
+
 # ---- stream-ordered device API (torch tensors) ------------------------------------------------------------------
 def _stream_handle(stream):
     import torch

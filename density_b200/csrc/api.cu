@@ -712,6 +712,114 @@ int density_b200_sharded_profile(density_b200_sharded* h, float* out_ms) {
     return DENSITY_B200_OK;
 }
 
+
+// ---- a reused Codec instance (streaming continuation) ---------------------------------------------------------------
+// /root/reference/src/codec/codec.rs:16,72,82: `encode` / `decode` are methods of an instance whose dictionary survives from call to
+// call until clear_state() (chameleon.rs:148-150, cheetah.rs:198-202, lion.rs:327-331); ProtectionState is created inside every call
+// (codec.rs:75,85). The state is kept the way the reference keeps it (65536 quads per table + last_hash) in device memory.
+struct density_b200_codec {
+    int alg = 0;
+    DevBuf state;       // scalar_codec.cu layout: status 256 B (last_hash at byte 192) + chunk_a + chunk_b + pred
+    DevBuf tables;      // Chameleon: carried-in table + this call's last-writer table (touched | fingerprint form)
+};
+
+density_b200_codec* density_b200_codec_create(int alg) {
+    g_last_error.clear();
+    if (alg < 0 || alg > 2) { set_error("bad algorithm id"); return nullptr; }
+    DeviceCtx* c = current_ctx();
+    if (!c) return nullptr;
+    density_b200_codec* h = new density_b200_codec();
+    h->alg = alg;
+    cudaError_t e = h->state.ensure(scalar_workspace_bytes(alg) + 256, c->stream);      // zeroed: X::new()
+    if (e == cudaSuccess && alg == ALG_CHAMELEON) e = h->tables.ensure(2 * 65536 * sizeof(uint32_t), c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_error("codec_create", e); h->state.release(); h->tables.release(); delete h; return nullptr; }
+    return h;
+}
+void density_b200_codec_destroy(density_b200_codec* h) {
+    if (!h) return;
+    h->state.release(); h->tables.release();
+    delete h;
+}
+int density_b200_codec_clear_state(density_b200_codec* h) {
+    g_last_error.clear();
+    DeviceCtx* c = current_ctx();
+    if (!h || !c) return DENSITY_B200_EARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaError_t e = cudaMemsetAsync(h->state.p, 0, scalar_workspace_bytes(h->alg) + 256, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_error("clear_state", e); return DENSITY_B200_ECUDA; }
+    return DENSITY_B200_OK;
+}
+
+// Codec::encode / Codec::decode on the instance: synchronous, host or device pointers, returns the bytes written (0 on error).
+static size_t codec_run(density_b200_codec* h, bool encode, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap) {
+    g_last_error.clear();
+    if (!h || (!in && n) || (!out && out_cap)) { set_error("null pointer"); return 0; }
+    if (n == 0) return 0;
+    DeviceCtx* c = current_ctx();
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const int alg = h->alg;
+    const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
+    cudaError_t e = cudaSuccess;
+    if (in_dev || out_dev) { e = cudaDeviceSynchronize(); if (e != cudaSuccess) { set_error("cudaDeviceSynchronize", e); return 0; } }
+    cudaStream_t st = c->stream;
+    if (!ws_acquire(c, st)) return 0;
+    const uint8_t* d_in = in; uint8_t* d_out = out; size_t d_cap = out_cap;
+    if (!in_dev) {
+        e = c->stage_in.ensure(n + 16, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->stage_in.p, in, n, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { set_error("H2D copy", e); return 0; }
+        d_in = c->stage_in.p;
+    }
+    if (!out_dev) {
+        d_cap = encode ? safe_size(alg, n) : out_cap;
+        e = c->stage_out.ensure(d_cap + 16, st);
+        if (e != cudaSuccess) { set_error("staging cudaMalloc", e); return 0; }
+        d_out = c->stage_out.p;
+    }
+    uint64_t launches = 0;
+    uint32_t* quads = reinterpret_cast<uint32_t*>(h->state.p + 256);      // chunk_a = Chameleon's chunk_map
+    bool done = false;
+    if (encode && alg == ALG_CHAMELEON && !(reinterpret_cast<uintptr_t>(d_in) & 3) && !(reinterpret_cast<uintptr_t>(d_out) & 1)) {
+        // run-parallel encoder with the instance's dictionary carried in; the state is only written back when the call succeeded
+        uint32_t* d_carry = reinterpret_cast<uint32_t*>(h->tables.p);
+        uint32_t* d_tab = d_carry + 65536;
+        ChamLayout L;
+        e = c->ws.ensure(cham_workspace_bytes(n, c->num_sms, &L), st);
+        c->layout = L;
+        const uint32_t nruns = cham_pick_runs(n, c->num_sms);
+        bool ok = false;
+        if (e == cudaSuccess) e = cham_quads_to_table(quads, d_carry, st, &launches);
+        if (e == cudaSuccess) e = cham_encode_phase1(d_in, n, c->ws.p, L, nruns, nullptr, st, &launches);
+        if (e == cudaSuccess) e = cham_encode_phase2_stream(d_in, n, c->ws.p, L, nruns, d_carry, d_out, d_cap, c->d_size, d_tab, 12, st, &launches, &ok);
+        if (e == cudaSuccess && ok) { e = cham_table_into_quads(d_tab, quads, st, &launches); done = true; }
+        c->last_was_chameleon_fastpath_capable = 0;
+    }
+    if (e == cudaSuccess && !done) {
+        // exact in-order kernel on the instance's state (Cheetah / Lion; Chameleon decode; a Chameleon encode whose copy map did not settle)
+        e = encode ? scalar_encode(alg, d_in, n, d_out, d_cap, h->state.p, c->d_size, st, &launches, nullptr, true)
+                   : scalar_decode(alg, d_in, n, d_out, d_cap, h->state.p, c->d_size, st, &launches, nullptr, true);
+    }
+    g_launches += launches;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_size, c->d_size, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    ws_release(c, st);
+    if (e != cudaSuccess) { set_error("codec call", e); return 0; }
+    const uint64_t produced = *c->h_size;
+    if (produced == 0) { set_error(encode ? "encode failed on device (output capacity?)" : "decode failed on device (malformed stream or output capacity)"); return 0; }
+    if (produced > out_cap) { set_error("output buffer too small"); return 0; }
+    if (!out_dev) {
+        e = cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("D2H copy", e); return 0; }
+    }
+    return (size_t)produced;
+}
+size_t density_b200_codec_encode(density_b200_codec* h, const uint8_t* in, size_t n, uint8_t* out, size_t cap) { return codec_run(h, true, in, n, out, cap); }
+size_t density_b200_codec_decode(density_b200_codec* h, const uint8_t* in, size_t n, uint8_t* out, size_t cap) { return codec_run(h, false, in, n, out, cap); }
+
 int density_b200_table_init(uint32_t* d_table, void* stream) {
     uint64_t l = 0;
     cudaError_t e = cham_table_init(d_table, reinterpret_cast<cudaStream_t>(stream), &l);

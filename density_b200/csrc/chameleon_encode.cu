@@ -124,9 +124,18 @@ __device__ __noinline__ void tile_in_order(FlagSmem& S, uint32_t* __restrict__ s
 //      the last member's value stays in the table. A misser without predecessor in a bucket this run has not touched yet cannot be
 //      decided here (the dictionary carried in from earlier runs is unknown): it goes to the run's unresolved list.
 // GENERIC = false: the tile is full and no block is in copy mode (the common case; no per-quad masks at all).
+#ifdef DNS_PHASE_TIMING
+#define DNS_PH(k) { const long long tn = clock64(); ph[k] += tn - tprev; tprev = tn; }
+#define DNS_PH_ARGS , long long (&ph)[8], long long& tprev
+#define DNS_PH_PASS , ph, tprev
+#else
+#define DNS_PH(k)
+#define DNS_PH_ARGS
+#define DNS_PH_PASS
+#endif
 template <bool GENERIC>
 __device__ __forceinline__ void flag_tile(FlagSmem& S, const uint32_t (&q)[FP_QPT], uint32_t rem, uint32_t run_q0, int buf,
-                                          uint2* __restrict__ unres_run, const uint8_t* __restrict__ cm_tile) {
+                                          uint2* __restrict__ unres_run, const uint8_t* __restrict__ cm_tile DNS_PH_ARGS) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t pos0 = warp * 128 + lane;
     uint32_t h[FP_QPT], f[FP_QPT];
@@ -174,7 +183,9 @@ __device__ __forceinline__ void flag_tile(FlagSmem& S, const uint32_t (&q)[FP_QP
             }
         }
     }
+    DNS_PH(0)
     __syncthreads();  // S1: all reads of tab / vbit precede the publishes; S.nrec = number of missers
+    DNS_PH(1)
     const uint32_t nmiss = S.nrec;  // stable until phase C appends behind it
 
     // ---- phase B: missers publish ---------------------------------------------------------------------------
@@ -188,7 +199,9 @@ __device__ __forceinline__ void flag_tile(FlagSmem& S, const uint32_t (&q)[FP_QP
         const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
         if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)i; else S.cls_overflow = 1;
     }
+    DNS_PH(2)
     __syncthreads();  // S2
+    DNS_PH(3)
 
     // ---- phase C: hit candidates read back ---------------------------------------------------------------------
     {
@@ -216,7 +229,9 @@ __device__ __forceinline__ void flag_tile(FlagSmem& S, const uint32_t (&q)[FP_QP
         }
         if (lane < FP_QPT) S.sigw[buf][warp * FP_QPT + lane] = lane == 0 ? fb[0] : lane == 1 ? fb[1] : lane == 2 ? fb[2] : fb[3];
     }
+    DNS_PH(4)
     __syncthreads();  // S3: class lists complete
+    DNS_PH(5)
 
     // ---- phase F: exact resolution of the listed quads ------------------------------------------------------------
     if (S.cls_overflow) {
@@ -302,7 +317,9 @@ __device__ __forceinline__ void flag_tile(FlagSmem& S, const uint32_t (&q)[FP_QP
         if (lane == 0) S.cls_count[warp] = 0;
         if (tid == 0) S.nrec = 0;
     }
+    DNS_PH(6)
     __syncthreads();  // S4: dictionary final for this tile, sigw[buf] final
+    DNS_PH(7)
 }
 
 // run r owns the tiles [run_tile_begin(r), run_tile_begin(r + 1))
@@ -355,6 +372,9 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 #pragma unroll
     for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < run_quads) ? ld_stream_u32(rin + pos0 + 32 * j) : 0u;
 
+#ifdef DNS_PHASE_TIMING
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
     #pragma unroll 1
     for (uint32_t lt = 0; lt < ntile_run; ++lt) {
         uint32_t q[FP_QPT];
@@ -377,9 +397,15 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         if (lt > 0 && tid < TILE_Q / 32) rsig[(lt - 1) * (TILE_Q / 32) + tid] = S.sigw[(lt - 1) & 1][tid];
 
         const int buf = (int)(lt & 1);
-        if (rcm != nullptr || rem < (uint32_t)TILE_Q) flag_tile<true>(S, q, rem, run_q0, buf, unres_run, rcm ? rcm + lt * 64 : nullptr);
-        else flag_tile<false>(S, q, rem, run_q0, buf, unres_run, nullptr);
+        if (rcm != nullptr || rem < (uint32_t)TILE_Q) flag_tile<true>(S, q, rem, run_q0, buf, unres_run, rcm ? rcm + lt * 64 : nullptr DNS_PH_PASS);
+        else flag_tile<false>(S, q, rem, run_q0, buf, unres_run, nullptr DNS_PH_PASS);
     }
+#ifdef DNS_PHASE_TIMING
+    if (run == 77 && (tid == 0 || tid == 32 * 17 + 5) && ntile_run) { const long long nt = (long long)ntile_run;
+        printf("run %u tid %u tiles %lld cycles/tile: A %lld |S1 %lld| B %lld |S2 %lld| C %lld |S3 %lld| F %lld |S4+loop top %lld|  total %lld\n", run, tid, nt,
+               ph[0] / nt, ph[1] / nt, ph[2] / nt, ph[3] / nt, ph[4] / nt, ph[5] / nt, ph[6] / nt, ph[7] / nt,
+               (ph[0] + ph[1] + ph[2] + ph[3] + ph[4] + ph[5] + ph[6] + ph[7]) / nt); }
+#endif
     if (ntile_run > 0 && tid < TILE_Q / 32) rsig[(ntile_run - 1) * (TILE_Q / 32) + tid] = S.sigw[(ntile_run - 1) & 1][tid];
 
     // ---- export the run's last-writer table ---------------------------------------------------------
@@ -951,6 +977,21 @@ __global__ void cham_table_fold_k(uint32_t* __restrict__ acc, const uint32_t* __
     if (i < 65536) { uint32_t v = next[i]; if (v & 0x10000u) acc[i] = v; }
 }
 
+// the dictionary as the reference keeps it (one quad per bucket, zero = never written unless it is bucket 0) <-> touched | fingerprint
+__global__ void cham_quads_to_table_k(const uint32_t* __restrict__ quads, uint32_t* __restrict__ t) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= 65536) return;
+    const uint32_t v = quads[h];
+    const uint32_t p = hash_prod(v);
+    t[h] = (prod_hash(p) == h) ? (0x10000u | prod_fp(p, v)) : 0u;   // a slot only ever holds a quad of its own bucket (chameleon.rs:95) or the initial 0
+}
+__global__ void cham_table_into_quads_k(const uint32_t* __restrict__ t, uint32_t* __restrict__ quads) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= 65536) return;
+    const uint32_t v = t[h];
+    if (v & 0x10000u) quads[h] = quad_from_hf(h, v & 0xFFFFu);
+}
+
 // carry-in dictionary of shard `rank` = left fold of the last-writer tables of the shards before it over the stream-start state
 // (one kernel for the whole fold; `tables` = [world][65536] as gathered over NVLink)
 __global__ void cham_rank_fold_k(const uint32_t* __restrict__ tables, uint32_t rank, uint32_t* __restrict__ carry) {
@@ -1142,7 +1183,8 @@ cudaError_t cham_phase2_rounds(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
 }
 
 cudaError_t cham_phase2_finish(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out, size_t cap,
-                               uint64_t* d_out_size, bool with_copy_map, cudaStream_t stream, uint64_t* launches, cudaEvent_t* ev) {
+                               uint64_t* d_out_size, bool with_copy_map, cudaStream_t stream, uint64_t* launches, cudaEvent_t* ev,
+                               bool inorder_fallback = true) {
     const uint64_t nblocks = (nbytes + 255) / 256;
     const uint32_t ntiles = (uint32_t)((nblocks + 63) / 64);
     const uint32_t ngroups = (ntiles + SCAN_G - 1) / SCAN_G;
@@ -1151,10 +1193,10 @@ cudaError_t cham_phase2_finish(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
     uint8_t* copymap = ws + L.copymap;
     if (with_copy_map) {
         // the exact in-order walk if the iteration did not settle; then the sizes again, now with the copy map
-        cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, st, 1, sigw, copymap);
+        if (inorder_fallback) { cham_protected_pass<<<1, 1024, sizeof(ProtSmem), stream>>>(reinterpret_cast<const uint32_t*>(d_in), nbytes, st, 1, sigw, copymap); ++*launches; }
         cham_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(sigw, copymap, nbytes, nblocks, ntiles, 1, 0, 0, st,
                                                               reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
-        *launches += 2;
+        ++*launches;
     }
     scan_groups_local<<<ngroups, SCAN_T, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.tile_bytes), ntiles,
                                                       reinterpret_cast<uint32_t*>(ws + L.tile_local),
@@ -1217,6 +1259,43 @@ cudaError_t cham_encode_phase2_blocking(const uint8_t* d_in, size_t nbytes, uint
     }
     if (e == cudaSuccess) e = cham_phase2_finish(d_in, nbytes, ws, L, d_out, cap, d_out_size, true, stream, launches, nullptr);
     return e;
+}
+
+// Phase 2 for a reused Codec instance: dictionary carried in, copy map by host-resumed iteration; when it does not settle nothing is
+// emitted and *ok = false (the caller runs the in-order kernel on the instance's state instead). On success d_table_out = this call's
+// last-writer table under the final copy map (copy-mode blocks never reach the dictionary, codec.rs:35-37).
+cudaError_t cham_encode_phase2_stream(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns, const uint32_t* d_carry_in,
+                                      uint8_t* d_out, size_t cap, uint64_t* d_out_size, uint32_t* d_table_out, int max_batches, cudaStream_t stream,
+                                      uint64_t* launches, bool* ok) {
+    *ok = true;
+    if (nbytes == 0) return cudaMemsetAsync(d_out_size, 0, sizeof(uint64_t), stream);
+    cudaError_t e = cham_phase2_begin(d_in, nbytes, ws, L, nruns, d_carry_in, false, stream, launches);
+    if (e == cudaSuccess) e = cham_phase2_rounds(d_in, nbytes, ws, L, nruns, d_carry_in, 0, PROT_ITERS, false, stream, launches);
+    bool more = false;
+    for (int batch = 0; e == cudaSuccess; ++batch) {
+        e = cham_phase2_needs_more(ws, L, stream, &more);
+        if (e != cudaSuccess || !more || batch >= max_batches) break;
+        e = cham_phase2_rounds(d_in, nbytes, ws, L, nruns, d_carry_in, 8, 15, true, stream, launches);
+    }
+    if (e != cudaSuccess) return e;
+    if (more) { *ok = false; return cudaSuccess; }
+    e = cham_phase2_finish(d_in, nbytes, ws, L, d_out, cap, d_out_size, true, stream, launches, nullptr, false);
+    if (e == cudaSuccess) {
+        cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), nullptr, 1, nruns, nullptr, d_table_out);
+        ++*launches;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+cudaError_t cham_quads_to_table(const uint32_t* d_quads, uint32_t* d_table, cudaStream_t stream, uint64_t* launches) {
+    cham_quads_to_table_k<<<65536 / 256, 256, 0, stream>>>(d_quads, d_table);
+    ++*launches;
+    return cudaGetLastError();
+}
+cudaError_t cham_table_into_quads(const uint32_t* d_table, uint32_t* d_quads, cudaStream_t stream, uint64_t* launches) {
+    cham_table_into_quads_k<<<65536 / 256, 256, 0, stream>>>(d_table, d_quads);
+    ++*launches;
+    return cudaGetLastError();
 }
 
 cudaError_t cham_status_accumulate(const uint8_t* ws, const ChamLayout& L, uint32_t* d_flag, cudaStream_t stream, uint64_t* launches) {

@@ -182,11 +182,14 @@ __global__ void dec_block_offsets(const uint8_t* __restrict__ in, uint64_t n, ui
 
 // ---- 2. quiet check + capacity check -------------------------------------------------------------------------------------------
 template <class T>
-__global__ void dec_quiet_check(const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, DecStatus* __restrict__ st, uint64_t cap) {
+__global__ void dec_quiet_check(const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, uint64_t maxblocks, DecStatus* __restrict__ st, uint64_t cap) {
     const uint64_t nb = st->main_blocks;
     const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (nb * T::BS > cap) { if (b == 0) st->error = 2; return; }  // DENSITY_B200_ECAPACITY (blk_off holds only what fits)
-    if (b >= nb) return;
+    // DENSITY_B200_ECAPACITY — unless the count is void because copy-mode blocks were misread as signatures: every block in front of the
+    // first copy-mode block is read correctly, and that includes the incompressible pair that started the episode, so the blocks that
+    // fit (blk_off holds no more) are enough to find it; dec_seq_walk then recounts and judges the capacity again
+    if (b == 0 && nb * T::BS > cap) st->error = 2;
+    if (b >= nb || b >= maxblocks) return;
     const bool inc = T::consumed(ldsig(in + blk_off[b])) >= T::BS;  // codec.rs:98
     if (b == nb - 1) st->last_main_inc = inc ? 1u : 0u;
     if (inc && b > 0) {
@@ -378,7 +381,7 @@ inline cudaError_t bounds_launch(const uint8_t* d_in, size_t nbytes, size_t cap,
     dec_top_walk<T><<<1, 32, 0, stream>>>(gres, ngroups, nbytes, g_entry, g_bb, st);
     dec_chunk_entries<T><<<(ngroups + 127) / 128, 128, 0, stream>>>(res, nchunks, g_entry, g_bb, ngroups, c_entry, c_bb, nullptr);
     dec_block_offsets<T><<<(nchunks + 127) / 128, 128, 0, stream>>>(d_in, nbytes, nchunks, c_entry, c_bb, blk_off, L.maxblocks, nullptr);
-    dec_quiet_check<T><<<(unsigned)((L.maxblocks + 255) / 256), 256, 0, stream>>>(d_in, blk_off, st, cap);
+    dec_quiet_check<T><<<(unsigned)((L.maxblocks + 255) / 256), 256, 0, stream>>>(d_in, blk_off, L.maxblocks, st, cap);
     // streams with copy-mode blocks only (the three kernels return at once otherwise): in-order walk, then the entries of the chunks of
     // jumped groups and the offsets of the blocks of jumped chunks
     dec_seq_walk<T><<<1, SW_THREADS, 0, stream>>>(d_in, nbytes, cap, nchunks, res, gres, ngroups, g_entry, g_bb, c_entry, c_bb, blk_off, L.maxblocks, st);

@@ -24,6 +24,15 @@ cudaError_t cham_encode_phase2_blocking(const uint8_t* d_in, size_t nbytes, uint
 cudaError_t cham_encode_protected_only(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint8_t* d_out,
                                        size_t cap, uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches);
 
+// streaming continuation (a reused Codec instance, codec.rs:16,72): the dictionary as the reference keeps it (65536 quads) <-> the
+// touched | fingerprint form of the run-parallel encoder; and phase 2 with a carried-in dictionary that gives up (no emit, *ok = false)
+// instead of walking in order when the copy map does not settle
+cudaError_t cham_quads_to_table(const uint32_t* d_quads, uint32_t* d_table, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_table_into_quads(const uint32_t* d_table, uint32_t* d_quads, cudaStream_t stream, uint64_t* launches);
+cudaError_t cham_encode_phase2_stream(const uint8_t* d_in, size_t nbytes, uint8_t* ws, const ChamLayout& L, uint32_t nruns, const uint32_t* d_carry_in,
+                                      uint8_t* d_out, size_t cap, uint64_t* d_out_size, uint32_t* d_table_out, int max_batches, cudaStream_t stream,
+                                      uint64_t* launches, bool* ok);
+
 // shared pieces of the encoders (chameleon_encode.cu)
 struct Status;
 cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* st, int it, uint8_t* inc,
@@ -55,9 +64,9 @@ const void* chee_decode_status_ptr(uint8_t* ws, size_t nbytes, size_t cap, int n
 // scalar_codec.cu (Cheetah / Lion, in-order)
 size_t scalar_workspace_bytes(int alg);
 cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if_zero = nullptr);
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if_zero = nullptr, bool keep_state = false);
 cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if = nullptr);
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if = nullptr, bool keep_state = false);
 // tail loop only (codec.rs:102-123), continuing from the state the parallel decoder left: tables already in `ws`, boundary status
 // (bounds::DecStatus: tail offset, block count, protection state) and the last hash (cheedec::ClStatus::final_ctx) on the device;
 // runs only if *d_skip_if == 0

@@ -78,12 +78,14 @@ struct Enc {
 
 template <int ALG>
 __global__ void encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, Tables T,
-                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if_zero) {
+                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if_zero,
+                              uint32_t* __restrict__ last_hash_io) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (run_if_zero && *run_if_zero != 0) return;   // the parallel encoder already produced the result
     constexpr uint32_t B = ALG == ALG_CHAMELEON ? 256 : ALG == ALG_CHEETAH ? 128 : 64;
     constexpr uint32_t SB = ALG == ALG_LION ? 6 : 8;
     Enc<ALG> E; E.T = T; E.out = out; E.cap = cap;
+    if (last_hash_io) E.last_hash = *last_hash_io;      // a reused Codec instance keeps last_hash (cheetah.rs:26, lion.rs:30)
     Protection ps; ps.init();
     const bool aligned4 = (reinterpret_cast<uintptr_t>(in) & 3) == 0;
     for (uint64_t off = 0; off < n && !E.overflow; off += B) {  // codec.rs:76
@@ -109,6 +111,7 @@ __global__ void encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_
     if (E.overflow) { status->error = 2; E.idx = 0; }
     status->out_bytes = E.idx;
     if (d_out_size) *d_out_size = E.idx;
+    if (last_hash_io) *last_hash_io = E.last_hash;
 }
 
 template <int ALG>
@@ -227,10 +230,12 @@ __device__ __forceinline__ void decode_loops(Dec<ALG>& D, Protection& ps, bool w
 
 template <int ALG>
 __global__ void decode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint64_t cap, Tables T,
-                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if) {
+                              Status* __restrict__ status, uint64_t* __restrict__ d_out_size, const uint32_t* __restrict__ run_if,
+                              uint32_t* __restrict__ last_hash_io) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (run_if && *run_if == 0) return;   // the parallel decoder already produced the result
     Dec<ALG> D; D.T = T; D.in = in; D.n = n; D.out = out; D.cap = cap;
+    if (last_hash_io) D.last_hash = *last_hash_io;
     Protection ps; ps.init();
     decode_loops<ALG>(D, ps, true);
     uint64_t res = D.oidx;
@@ -238,6 +243,7 @@ __global__ void decode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_
     else if (D.overflow) { status->error = 2; res = 0; }
     status->out_bytes = res;
     if (d_out_size) *d_out_size = res;
+    if (last_hash_io) *last_hash_io = D.last_hash;
 }
 
 // the boundary status block of decode_bounds.cuh and the iteration status of cl_decode.cu, as far as the tail needs them
@@ -282,31 +288,34 @@ static scalar::Tables carve(int alg, uint8_t* ws) {
     return T;
 }
 
+// keep_state: `ws` is the state of a reused Codec instance (tables + last_hash at byte 192): nothing is cleared except the status words
 cudaError_t scalar_encode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if_zero) {
-    cudaError_t e = cudaMemsetAsync(ws, 0, scalar_workspace_bytes(alg), stream);  // X::new(): zeroed tables
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if_zero, bool keep_state) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, keep_state ? 128 : scalar_workspace_bytes(alg), stream);  // X::new(): zeroed tables
     if (e != cudaSuccess) return e;
     scalar::Tables T = carve(alg, ws);
     Status* st = reinterpret_cast<Status*>(ws);
+    uint32_t* lh = keep_state ? reinterpret_cast<uint32_t*>(ws + 192) : nullptr;
     switch (alg) {
-    case ALG_CHAMELEON: scalar::encode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero); break;
-    case ALG_CHEETAH:   scalar::encode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero); break;
-    default:            scalar::encode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero); break;
+    case ALG_CHAMELEON: scalar::encode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero, lh); break;
+    case ALG_CHEETAH:   scalar::encode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero, lh); break;
+    default:            scalar::encode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if_zero, lh); break;
     }
     ++*launches;
     return cudaGetLastError();
 }
 
 cudaError_t scalar_decode(int alg, const uint8_t* d_in, size_t nbytes, uint8_t* d_out, size_t cap, uint8_t* ws,
-                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if) {
-    cudaError_t e = cudaMemsetAsync(ws, 0, scalar_workspace_bytes(alg), stream);
+                          uint64_t* d_out_size, cudaStream_t stream, uint64_t* launches, const uint32_t* d_run_if, bool keep_state) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, keep_state ? 128 : scalar_workspace_bytes(alg), stream);
     if (e != cudaSuccess) return e;
     scalar::Tables T = carve(alg, ws);
     Status* st = reinterpret_cast<Status*>(ws);
+    uint32_t* lh = keep_state ? reinterpret_cast<uint32_t*>(ws + 192) : nullptr;
     switch (alg) {
-    case ALG_CHAMELEON: scalar::decode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
-    case ALG_CHEETAH:   scalar::decode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
-    default:            scalar::decode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if); break;
+    case ALG_CHAMELEON: scalar::decode_kernel<ALG_CHAMELEON><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if, lh); break;
+    case ALG_CHEETAH:   scalar::decode_kernel<ALG_CHEETAH><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if, lh); break;
+    default:            scalar::decode_kernel<ALG_LION><<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, T, st, d_out_size, d_run_if, lh); break;
     }
     ++*launches;
     return cudaGetLastError();

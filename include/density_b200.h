@@ -149,6 +149,24 @@ DENSITY_B200_API int density_b200_encode_sharded(density_b200_sharded*, const ui
 /* stage times (ms) of the last call: [0] flag pass, [1] table exchange + fold, [2] carry / resolve / sizes / scan, [3] emit, [4] seams + gather */
 DENSITY_B200_API int density_b200_sharded_profile(density_b200_sharded*, float* out_ms5);
 
+/*
+ * A reused Codec INSTANCE (streaming continuation). In the reference `encode` / `decode` are methods of an instance
+ * (/root/reference/src/codec/codec.rs:16,72,82) whose dictionary survives from call to call until clear_state()
+ * (chameleon.rs:148-150, cheetah.rs:198-202, lion.rs:327-331), while the protection state is created inside every call
+ * (codec.rs:75,85); the nine symbols above build a fresh instance per call (chameleon.rs:45-53). These mirror the instance:
+ *   density_b200_codec_create(alg)  = X::new()        density_b200_codec_clear_state = Codec::clear_state
+ *   density_b200_codec_encode       = Codec::encode   density_b200_codec_decode      = Codec::decode
+ * Synchronous, host or device pointers, bytes written or 0 on error. Chameleon encode runs the run-parallel kernels with the
+ * instance's dictionary carried in (buffers larger than HBM can be encoded piecewise, bit-exact with an instance on the CPU);
+ * Cheetah / Lion and every decode run the exact in-order kernel on the instance's tables.
+ */
+typedef struct density_b200_codec density_b200_codec; /* opaque */
+DENSITY_B200_API density_b200_codec* density_b200_codec_create(int alg);
+DENSITY_B200_API void density_b200_codec_destroy(density_b200_codec*);
+DENSITY_B200_API int density_b200_codec_clear_state(density_b200_codec*);
+DENSITY_B200_API size_t density_b200_codec_encode(density_b200_codec*, const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+DENSITY_B200_API size_t density_b200_codec_decode(density_b200_codec*, const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+
 /* ---- per-stage device timing of the last Chameleon encode on the current device ------- */
 /* When enabled, density_b200_encode_device records CUDA events on the caller's stream around the flag pass
    and the emit pass of every call (ring of 64 calls; enable(1) resets it). density_b200_profile_get waits

@@ -42,8 +42,47 @@ def lib():
         L.oracle_encode_stats.restype = ctypes.c_size_t
         L.oracle_encode_stats.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]
+        L.oracle_codec_new.restype = ctypes.c_void_p
+        L.oracle_codec_new.argtypes = [ctypes.c_int]
+        L.oracle_codec_free.restype = None
+        L.oracle_codec_free.argtypes = [ctypes.c_void_p]
+        L.oracle_codec_clear_state.restype = None
+        L.oracle_codec_clear_state.argtypes = [ctypes.c_void_p]
+        for name in ("oracle_codec_encode", "oracle_codec_decode"):
+            f = getattr(L, name)
+            f.restype = ctypes.c_size_t
+            f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
         _lib = L
     return _lib
+
+
+class Codec:
+    """A reference Codec INSTANCE that is reused across calls (codec.rs:16,72,82): the dictionary survives until clear_state()."""
+
+    def __init__(self, alg):
+        self.alg = alg
+        self._h = lib().oracle_codec_new(ALGS[alg])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_codec_free(self._h)
+            self._h = None
+
+    def clear_state(self):
+        lib().oracle_codec_clear_state(self._h)
+
+    def encode(self, data):
+        a = _as_u8(data)
+        cap = safe_encode_buffer_size(self.alg, a.size)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        n = lib().oracle_codec_encode(self._h, a.ctypes.data, a.size, out.ctypes.data, cap)
+        return out[:n].copy()
+
+    def decode(self, data, out_size):
+        a = _as_u8(data)
+        out = np.empty(max(out_size, 1), dtype=np.uint8)
+        n = lib().oracle_codec_decode(self._h, a.ctypes.data, a.size, out.ctypes.data, out_size)
+        return out[:n].copy()
 
 
 def safe_encode_buffer_size(alg, size):

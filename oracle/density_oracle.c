@@ -416,6 +416,26 @@ size_t oracle_decode(int alg, const uint8_t *in, size_t n, uint8_t *out, size_t 
     size_t r = codec_decode(&c, in, n, out, cap);
     codec_free(&c); return r;
 }
+/* ---- Codec INSTANCE reuse (codec.rs:16,72,82: `encode` / `decode` are &mut self methods; the inherent X::encode builds a fresh
+   instance per call, a caller that keeps one gets a dictionary that survives from call to call until clear_state();
+   ProtectionState is created inside every call, codec.rs:75,85) ------------------------------------------------------------------ */
+void *oracle_codec_new(int alg) {
+    codec_t *c = (codec_t *)malloc(sizeof(codec_t));
+    if (!c) return NULL;
+    if (codec_init(c, alg)) { codec_free(c); free(c); return NULL; }
+    return c;
+}
+void oracle_codec_free(void *h) { if (h) { codec_free((codec_t *)h); free(h); } }
+void oracle_codec_clear_state(void *h) { /* chameleon.rs:148-150, cheetah.rs:198-202, lion.rs:327-331 */
+    codec_t *c = (codec_t *)h;
+    c->last_hash = 0;
+    memset(c->chunk_a, 0, sizeof(uint32_t) << 16);
+    if (c->chunk_b) memset(c->chunk_b, 0, sizeof(uint32_t) << 16);
+    if (c->pred) memset(c->pred, 0, (sizeof(uint32_t) * (c->alg == ALG_LION ? 5 : 1)) << 16);
+}
+size_t oracle_codec_encode(void *h, const uint8_t *in, size_t n, uint8_t *out, size_t cap) { return codec_encode((codec_t *)h, in, n, out, cap, NULL); }
+size_t oracle_codec_decode(void *h, const uint8_t *in, size_t n, uint8_t *out, size_t cap) { return codec_decode((codec_t *)h, in, n, out, cap); }
+
 /* encode + number of copy-mode blocks (diagnostic for the tests; not in the reference ABI) */
 size_t oracle_encode_stats(int alg, const uint8_t *in, size_t n, uint8_t *out, size_t cap, uint64_t *copied_blocks) {
     codec_t c; if (codec_init(&c, alg)) { codec_free(&c); return 0; }

@@ -656,3 +656,34 @@ def test_encode_sharded_two_ranks_nccl_equals_oracle(torch_cuda, codecs):
     cat = np.concatenate([got[r][1] for r in range(world)])
     assert cat.size == want.size and (cat == want).all()
     assert got[0][2] == want.size and (got[0][3] == want).all()
+
+
+@pytest.mark.parametrize("alg", ALGS)
+def test_codec_instance_streaming_continuation(torch_cuda, codecs, alg):
+    """density_b200_codec_* (a reused Codec instance, codec.rs:16,72,82) against an oracle instance that is reused the same way: three
+    pieces encoded one after the other (text, a piece with copy-mode blocks, text again), decoded by a second instance, then
+    clear_state() and a fresh start. Chameleon encode takes the run-parallel kernels with the dictionary carried in."""
+    from density_b200.codec import CodecInstance
+    from density_b200 import synth
+    big = alg == "chameleon"
+    pieces = [synth.synth_text((3 << 20) + 5 if big else 150001).numpy(),
+              synth.synth_mixed((2 << 20) + 256 * 3 if big else 120000).numpy(),
+              synth.synth_text((1 << 20) + 77 if big else 70001, first_page=9).numpy()]
+    want_inst = oracle.Codec(alg)
+    enc, dec = CodecInstance(alg), CodecInstance(alg)
+    streams = []
+    for p in pieces:
+        want = want_inst.encode(p)
+        out = np.zeros(codecs[alg].safe_encode_buffer_size(p.size), dtype=np.uint8)
+        n = enc.encode(p, out)
+        assert n == want.size and (out[:n] == want).all(), (alg, p.size)
+        streams.append(out[:n].copy())
+    for p, s in zip(pieces, streams):
+        back = np.zeros(p.size, dtype=np.uint8)
+        assert dec.decode(s, back) == p.size and (back == p).all()
+    enc.clear_state()
+    out = np.zeros(codecs[alg].safe_encode_buffer_size(pieces[2].size), dtype=np.uint8)
+    n = enc.encode(pieces[2], out)
+    want = oracle.encode(alg, pieces[2])
+    assert n == want.size and (out[:n] == want).all()
+    enc.close(); dec.close()

@@ -87,3 +87,19 @@ def test_copy_mode_engages_on_random():
 def test_undersized_output_reports_zero():
     data = payload("random", 4096, 1)
     assert oracle.encode("chameleon", data, cap=100).size == 0
+
+
+@pytest.mark.parametrize("alg", ["chameleon", "cheetah", "lion"])
+def test_codec_instance_keeps_its_dictionary(alg, dickens200k):
+    """codec.rs:16,72,82: `encode` / `decode` are methods of an instance; the dictionary survives from call to call until clear_state()
+    (chameleon.rs:148-150), the protection state is fresh in every call (codec.rs:75,85)."""
+    a, b = dickens200k[:70000], dickens200k[70000:150001]
+    inst = oracle.Codec(alg)
+    ea, eb = inst.encode(a), inst.encode(b)
+    assert (ea == oracle.encode(alg, a)).all()                       # a fresh instance behaves like the inherent X::encode
+    fresh_b = oracle.encode(alg, b)
+    assert eb.size != fresh_b.size or (eb != fresh_b).any()          # the second call saw the first call's dictionary
+    dec = oracle.Codec(alg)
+    assert (dec.decode(ea, a.size) == a).all() and (dec.decode(eb, b.size) == b).all()
+    inst.clear_state()
+    assert (inst.encode(b) == fresh_b).all()

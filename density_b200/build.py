@@ -40,8 +40,10 @@ def build(force=False, verbose=False):
         cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static", "-o", SO] + objs
+    tmp = SO + ".tmp"     # link next to the target, then rename: a snapshot of the tree never sees a half-written library
+    cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static", "-o", tmp] + objs
     subprocess.check_call(cmd)
+    os.replace(tmp, SO)
     return SO
 
 

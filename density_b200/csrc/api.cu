@@ -69,6 +69,7 @@ struct DeviceCtx {
     uint64_t prof_count = 0;           // encodes recorded since profile_enable(1)
     // One workspace per device: a call may only start using it when the previous call (on whatever stream) has finished with it.
     // Every enqueue ends with cudaEventRecord(ws_free, its stream) and starts with cudaStreamWaitEvent(its stream, ws_free).
+    const void* last_cl_status = nullptr;   // iteration status block of the last parallel Cheetah decode (diagnostics)
     cudaEvent_t ws_free = nullptr;
     bool ws_free_recorded = false;
     std::mutex mu;
@@ -257,6 +258,7 @@ static int decode_device_locked_impl(DeviceCtx* c, int alg, const uint8_t* d_in,
         if (e == cudaSuccess) {
             const void* cl_st = nullptr;
             const void* b_st = chee_decode_status_ptr(c->ws.p, n, cap, c->num_sms, &cl_st);
+            c->last_cl_status = cl_st;
             e = scalar_decode_tail(alg, d_in, n, d_out, cap, tail_ws, b_st, cl_st, d_out_size, stream, &launches, d_fallback);
         }
         if (e == cudaSuccess && path != 1)
@@ -915,6 +917,18 @@ void density_b200_shutdown(void) {
         c.d_size = nullptr; c.h_size = nullptr; c.stream = nullptr; c.ready = false;
     }
     if (cur >= 0) cudaSetDevice(cur);
+}
+
+/* diagnostic: the context iteration of the last parallel Cheetah decode on the current device (synchronises):
+   out4 = {rounds used, settled (0 = the in-order kernel had to take over), contexts of the final sweep's last hash, round budget} */
+int density_b200_cheetah_decode_rounds(uint32_t* out4) {
+    DeviceCtx* c = current_ctx();
+    if (!c || !c->last_cl_status || !out4) return DENSITY_B200_EARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    unsigned int raw[8] = {0};
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(raw, c->last_cl_status, sizeof raw, cudaMemcpyDeviceToHost) != cudaSuccess) return DENSITY_B200_ECUDA;
+    out4[0] = raw[3]; out4[1] = raw[2] && !raw[5]; out4[2] = raw[4]; out4[3] = 24;
+    return DENSITY_B200_OK;
 }
 
 /* test hook: rounds per stage of the Cheetah / Lion copy-map iteration (1..7; 7 = default) */

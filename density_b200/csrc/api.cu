@@ -920,14 +920,14 @@ void density_b200_shutdown(void) {
 }
 
 /* diagnostic: the context iteration of the last parallel Cheetah decode on the current device (synchronises):
-   out4 = {rounds used, settled (0 = the in-order kernel had to take over), contexts of the final sweep's last hash, round budget} */
+   out4 = {rounds used, settled (0 = the in-order kernel had to take over), run walks after round 0 (of rounds x runs), round budget} */
 int density_b200_cheetah_decode_rounds(uint32_t* out4) {
     DeviceCtx* c = current_ctx();
     if (!c || !c->last_cl_status || !out4) return DENSITY_B200_EARG;
     std::lock_guard<std::mutex> lk(c->mu);
     unsigned int raw[8] = {0};
     if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(raw, c->last_cl_status, sizeof raw, cudaMemcpyDeviceToHost) != cudaSuccess) return DENSITY_B200_ECUDA;
-    out4[0] = raw[3]; out4[1] = raw[2] && !raw[5]; out4[2] = raw[4]; out4[3] = 24;
+    out4[0] = raw[3]; out4[1] = raw[2] && !raw[5]; out4[2] = raw[6]; out4[3] = 40;
     return DENSITY_B200_OK;
 }
 

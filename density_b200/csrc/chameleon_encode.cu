@@ -39,62 +39,60 @@ namespace cham {
 // Pass 1: flag pass
 // ------------------------------------------------------------------------------------------------------
 constexpr int FP_THREADS = 1024;
-constexpr int FP_QPT = 8;                          // quads per thread per tile
-constexpr int TILE_Q = FP_THREADS * FP_QPT;        // 8192 quads = 32 KiB = 128 blocks (two 64-block tiles of the sizes / emit kernels)
-constexpr int WARP_Q = 32 * FP_QPT;                // a warp owns 256 consecutive quads of the tile: lane l holds quads l, l + 32, ... (a ballot is half a signature)
-constexpr int SIDE_N = 2048;                       // first-misser table (u32), indexed by hash & (SIDE_N-1)
+constexpr int FP_QPT = 4;                          // quads per thread per tile
+constexpr int TILE_Q = FP_THREADS * FP_QPT;        // 4096 quads = 16 KiB = 64 blocks
+constexpr int SIDE_N = 8192;                       // first-misser table (u32), indexed by hash & (SIDE_N-1)
 constexpr uint32_t SIDE_EMPTY = 0xFFFFFFFFu;
 
-constexpr int CLS_N = 32;                          // exact-path classes: class = hash >> 11, one warp each
-constexpr int CLS_CAP = 256;                       // entries per class list (32 x 256 = a whole tile); overflow -> in-order tile fallback
-constexpr int UNRES_PER_CLASS = 2048;              // a run's unresolved list = 32 class sublists: at most one first touch per bucket and run
+constexpr int CLS_N = 32;                          // slow-path classes: class = hash >> 11, one warp each
+constexpr int CLS_CAP = 128;                       // entries per class list; overflow -> in-order tile fallback
 
-// Per-tile record of a quad that takes the exact path (a misser, or a hit candidate whose bucket a misser wrote before it):
+// Compacted per-tile record of a misser (or of a hit member that turned out to need the slow path):
 //   x = hash | fp << 16
-//   y = pos(13) | touched << 13 | misser << 14 | old_fp << 16
-constexpr uint32_t R_POS = 0x1FFFu, R_TOUCHED = 1u << 13, R_MISSER = 1u << 14;
+//   y = pos(12) | touched << 12 | slow << 13 | first << 14 | setter << 15 | old_fp << 16
+constexpr uint32_t R_TOUCHED = 1u << 12, R_SLOW = 1u << 13, R_FIRST = 1u << 14;
 
 struct FlagSmem {
     uint16_t tab[65536];          // fingerprint of the last quad seen in each bucket
     uint32_t vbit[2048];          // "bucket touched" for the one case tab cannot express (fingerprint 0)
+    uint32_t conf[2048];          // per-tile conflict bits (bucket interleaves different values)
     uint32_t side[SIDE_N];        // per-tile min over missers of (pos << 16 | hash)
-    uint2 rec[TILE_Q];            // warp w owns rec[w * 256 ...): its missers from the front (phase A), its affected hit candidates behind
-                                  // them (phase C) — a quad has at most one record, so a region never overflows and nobody needs an atomic
-    uint16_t cls_list[CLS_N][CLS_CAP];  // record indices of the members of each class (unordered)
+    uint2 rec[TILE_Q];            // records: missers (phase A) then slow hit members (phase C); quad staging in the fallback
+    uint16_t cls_list[CLS_N][CLS_CAP];  // record indices of the slow members of each class (unordered)
     uint32_t cls_count[CLS_N];
-    uint32_t sigw[2][TILE_Q / 32];   // flag bits of the tile (double buffered: tile t's words leave for HBM during tile t+1)
-    uint32_t unres_cnt[CLS_N];       // fill of the run's unresolved sublists (only warp c appends to sublist c)
+    uint32_t sigw[TILE_Q / 32];   // flag bits of the tile: word (w*4+j) = sub-row j of warp w
+    uint32_t nrec;
+    uint32_t unres_count;
     uint32_t cls_overflow;
 };
 static_assert(sizeof(FlagSmem) <= 227 * 1024, "flag pass shared memory");
 
 __device__ __forceinline__ bool bit_test(const uint32_t* bm, uint32_t i) { return (bm[i >> 5] >> (i & 31)) & 1u; }
 
-// Append the lanes with `pred` set to sublist `cls` of the run's unresolved list. Called by all 32 lanes of the ONE warp that owns the
-// sublist at this point (phase F: warp cls; in-order fallback: warp 0 on its own), so the counter needs no atomic.
-__device__ __forceinline__ void append_unres_class(FlagSmem& S, uint32_t cls, bool pred, uint32_t qidx_in_run, uint32_t h, uint32_t f,
-                                                   uint2* __restrict__ unres_run) {
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
+// Append the lanes with `pred` set to the run's unresolved list (warp-aggregated). Must be called by all 32 lanes.
+__device__ __forceinline__ void append_unres(bool pred, uint32_t qidx_in_run, uint32_t h, uint32_t f,
+                                             uint32_t* s_count, uint2* __restrict__ unres_run) {
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
     if (m == 0) return;
-    const uint32_t base = S.unres_cnt[cls];
+    uint32_t base = 0;
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane == 0) base = atomicAdd(s_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (pred) {
-        const uint32_t idx = base + __popc(m & lanemask_lt());
-        if (idx < (uint32_t)UNRES_PER_CLASS) unres_run[cls * UNRES_PER_CLASS + idx] = make_uint2(qidx_in_run, h | (f << 16));
+        uint32_t idx = base + __popc(m & lanemask_lt());
+        if (idx < 65536u) unres_run[idx] = make_uint2(qidx_in_run, h | (f << 16));
     }
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) S.unres_cnt[cls] = base + __popc(m);
-    __syncwarp();
 }
 
 // In-order walk of one whole tile by one warp, from the (restored) pre-tile dictionary. Fallback for tiles whose
 // class lists overflow (adversarial inputs: hundreds of interleaving quads in a handful of buckets).
-__device__ __noinline__ void tile_in_order(FlagSmem& S, uint32_t* __restrict__ sig, const uint32_t* __restrict__ qg, uint32_t rem, uint32_t run_q0,
+__device__ __noinline__ void tile_in_order(FlagSmem& S, const uint32_t* qs, uint32_t rem, uint32_t run_q0,
                                            uint2* __restrict__ unres_run, const uint8_t* __restrict__ cm_tile) {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t c = 0; c < TILE_Q / 32; ++c) {
         const uint32_t pos = c * 32 + lane;
         const bool valid = pos < rem && !(cm_tile && cm_tile[pos >> 6]);   // copy-mode blocks never touch the dictionary (codec.rs:35-37)
-        const uint32_t q = pos < rem ? qg[pos] : 0u;
+        const uint32_t q = qs[pos];
         const uint32_t p = hash_prod(q);
         const uint32_t hh = valid ? prod_hash(p) : 0x10000u + lane;
         const uint32_t ff = prod_fp(p, q);
@@ -111,232 +109,17 @@ __device__ __noinline__ void tile_in_order(FlagSmem& S, uint32_t* __restrict__ s
             if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
         }
         const uint32_t fb = __ballot_sync(0xFFFFFFFFu, hit);
-        if (lane == 0) sig[c] = fb;
-        // first touches: one class at a time (the sublists are per class); a 32-quad step rarely has more than one
-        uint32_t todo = __ballot_sync(0xFFFFFFFFu, valid && !lower && !touched);
-        while (todo) {
-            const uint32_t cls = __shfl_sync(0xFFFFFFFFu, hh >> 11, __ffs(todo) - 1);
-            const bool mine = valid && !lower && !touched && (hh >> 11) == cls;
-            append_unres_class(S, cls, mine, run_q0 + pos, hh, ff, unres_run);
-            todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
-        }
+        if (lane == 0) S.sigw[c] = fb;
+        append_unres(valid && !lower && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
         __syncwarp();
     }
 }
-
-#ifdef DNS_PHASE_TIMING
-#define DNS_PH(k) { const long long tn = clock64(); ph[k] += tn - tprev; tprev = tn; }
-#define DNS_PH_ARGS , long long (&ph)[8], long long& tprev
-#define DNS_PH_PASS , ph, tprev
-#else
-#define DNS_PH(k)
-#define DNS_PH_ARGS
-#define DNS_PH_PASS
-#endif
-
-// One tile of the flag pass: four barrier-separated phases (protocol validated against the in-order walk by tools/proto_tile_protocol_v2.py).
-//   A  every quad reads old = tab[h]; old == f -> hit candidate, else misser (~8 % on text). A warp writes its missers' records into
-//      its own record region (ballot prefix, no atomics).
-//   B  missers publish f (racy on purpose: the bucket now holds SOME misser's value, which differs from the pre-tile value),
-//      atomicMin(side[h & (SIDE_N-1)], pos << 16 | h) (first misser of the bucket) and join their hash-class list.
-//   C  hit candidates re-read tab[h]: unchanged -> flag 1 (no misser in my bucket). Changed -> flag 1 if every misser of my bucket
-//      comes later (side slot), else the quad gets a record behind the warp's missers and joins the class list as well.
-//   F  warp w resolves class w exactly: predecessor = same-bucket member with the largest smaller position, else the pre-tile value;
-//      the last member's value stays in the table. A misser without predecessor in a bucket this run has not touched yet cannot be
-//      decided here (the dictionary carried in from earlier runs is unknown): it goes to the run's unresolved list.
-// GENERIC = false: the tile is full and no block is in copy mode (the common case; no per-quad masks at all).
-template <bool GENERIC>
-__device__ __forceinline__ void flag_tile(FlagSmem& S, const uint32_t (&q)[FP_QPT], const uint32_t* __restrict__ qg, uint32_t rem, uint32_t run_q0, int buf,
-                                          uint2* __restrict__ unres_run, const uint8_t* __restrict__ cm_tile DNS_PH_ARGS) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t pos0 = warp * WARP_Q + lane;
-    const uint32_t wbase = warp * WARP_Q;            // my warp's record region
-    const uint32_t lt_mask = lanemask_lt();
-    uint32_t h[FP_QPT], f[FP_QPT];
-    uint32_t actmask = (1u << FP_QPT) - 1u;          // bit j: my sub-row j quad exists and its block is not in copy mode
-    if (GENERIC) {
-        uint32_t cp = 0;                             // bit k: block 4 * warp + k of this tile is a copy-mode block
-        if (cm_tile) {
-#pragma unroll
-            for (int k = 0; k < FP_QPT / 2; ++k) cp |= (cm_tile[warp * (FP_QPT / 2) + k] ? 1u : 0u) << k;
-        }
-        actmask = 0;
-#pragma unroll
-        for (int j = 0; j < FP_QPT; ++j)
-            if (pos0 + 32 * j < rem && !((cp >> (j >> 1)) & 1u)) actmask |= 1u << j;
-    }
-    // ---- phase A ----------------------------------------------------------------------------------------
-    uint32_t missmask = 0, wcnt = 0;                 // wcnt: records in my warp's region so far (warp-uniform)
-    {
-        uint32_t old[FP_QPT];
-#pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            const uint32_t p = hash_prod(q[j]);
-            h[j] = prod_hash(p);
-            f[j] = prod_fp(p, q[j]);
-            old[j] = S.tab[h[j]];
-        }
-#pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            bool miss = old[j] != f[j];
-            if (f[j] == 0 && !miss) miss = !bit_test(S.vbit, h[j]);     // fingerprint 0 == "empty": the touched bit decides (rare)
-            if (GENERIC) miss = miss && ((actmask >> j) & 1u);
-            const uint32_t mb = __ballot_sync(0xFFFFFFFFu, miss);
-            if (miss) {
-                missmask |= 1u << j;
-                uint32_t y = (pos0 + 32 * j) | R_MISSER | R_TOUCHED | (old[j] << 16);
-                if (old[j] == 0 && !bit_test(S.vbit, h[j])) y &= ~R_TOUCHED;
-                S.rec[wbase + wcnt + __popc(mb & lt_mask)] = make_uint2(h[j] | (f[j] << 16), y);
-            }
-            wcnt += __popc(mb);
-        }
-    }
-    const uint32_t wmiss = wcnt;
-    DNS_PH(0)
-    __syncthreads();  // S1: all reads of tab / vbit precede the publishes
-    DNS_PH(1)
-
-    // ---- phase B: my warp's missers publish --------------------------------------------------------------------
-    #pragma unroll 1
-    for (uint32_t i = lane; i < wmiss; i += 32) {
-        const uint2 r = S.rec[wbase + i];
-        const uint32_t hh = r.x & 0xFFFFu;
-        S.tab[hh] = (uint16_t)(r.x >> 16);  // racy between different values on purpose
-        atomicMin(&S.side[hh & (SIDE_N - 1)], ((r.y & R_POS) << 16) | hh);
-        const uint32_t c = hh >> 11;
-        const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
-        if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)(wbase + i); else S.cls_overflow = 1;
-    }
-    DNS_PH(2)
-    __syncthreads();  // S2
-    DNS_PH(3)
-
-    // ---- phase C: hit candidates read back ---------------------------------------------------------------------
-    {
-        uint32_t mysig = 0;                          // lane j keeps the ballot of sub-row j
-#pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) {
-            const bool cand = (!GENERIC || ((actmask >> j) & 1u)) && !(missmask & (1u << j));
-            bool ok = cand && S.tab[h[j]] == f[j];
-            const uint32_t pos = pos0 + 32 * j;
-            if (cand && !ok) {
-                const uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
-                ok = (slot & 0xFFFFu) == h[j] && pos < (slot >> 16);      // every misser of my bucket comes after me
-            }
-            const uint32_t fb = __ballot_sync(0xFFFFFFFFu, ok);
-            if ((int)lane == j) mysig = fb;
-            const bool affected = cand && !ok;
-            const uint32_t am = __ballot_sync(0xFFFFFFFFu, affected);
-            if (am) {
-                if (affected) {
-                    const uint32_t idx = wbase + wcnt + __popc(am & lt_mask);
-                    S.rec[idx] = make_uint2(h[j] | (f[j] << 16), pos | R_TOUCHED | (f[j] << 16));
-                    const uint32_t c = h[j] >> 11;
-                    const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
-                    if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)idx; else S.cls_overflow = 1;
-                }
-                wcnt += __popc(am);
-            }
-        }
-        if (lane < FP_QPT) S.sigw[buf][warp * FP_QPT + lane] = mysig;
-    }
-    DNS_PH(4)
-    __syncthreads();  // S3: class lists complete
-    DNS_PH(5)
-
-    // ---- phase F: exact resolution of the listed quads ------------------------------------------------------------
-    if (S.cls_overflow) {
-        // restore the pre-tile dictionary (only missers wrote), clear the per-tile state, walk the tile in order
-        #pragma unroll 1
-        for (uint32_t i = lane; i < wmiss; i += 32) {
-            const uint2 r = S.rec[wbase + i];
-            S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
-            S.side[(r.x & 0xFFFFu) & (SIDE_N - 1)] = SIDE_EMPTY;
-        }
-        if (tid < CLS_N) S.cls_count[tid] = 0;
-        __syncthreads();
-        if (tid == 0) S.cls_overflow = 0;
-        if (warp == 0) tile_in_order(S, S.sigw[buf], qg, rem, run_q0, unres_run, cm_tile);
-    } else {
-        const uint32_t n = S.cls_count[warp];
-        const uint16_t* __restrict__ lst = S.cls_list[warp];
-        if (n != 0 && n <= 32) {
-            // the whole class in one warp: same-bucket groups from match_any, predecessor by a walk over the (small) group
-            const bool valid = lane < n;
-            uint32_t pos = 0, hh = 0x10000u + lane, ff = 0, oldv = 0, fl = 0;
-            if (valid) {
-                const uint2 d = S.rec[lst[lane]];
-                hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & R_POS; fl = d.y; oldv = d.y >> 16;
-            }
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, hh);
-            uint32_t others = grp & ~(1u << lane);
-            int best = -1; uint32_t bestf = 0; bool later = false;
-            while (__any_sync(0xFFFFFFFFu, others != 0)) {
-                const int src = others ? __ffs(others) - 1 : (int)lane;
-                const uint32_t pk = __shfl_sync(0xFFFFFFFFu, pos, src), fk = __shfl_sync(0xFFFFFFFFu, ff, src);
-                if (others) {
-                    if (pk < pos && (int)pk > best) { best = (int)pk; bestf = fk; }
-                    later |= pk > pos;
-                    others &= others - 1;
-                }
-            }
-            const bool touched = (fl & R_TOUCHED) != 0;
-            const bool hit = valid && (best >= 0 ? (bestf == ff) : (touched && oldv == ff));
-            if (hit) atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
-            if (valid && !later) {
-                S.tab[hh] = (uint16_t)ff;
-                if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-            }
-            if (valid && (fl & R_MISSER)) S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
-            append_unres_class(S, warp, valid && best < 0 && !touched, run_q0 + pos, hh, ff, unres_run);
-        } else if (n != 0) {
-            #pragma unroll 1
-            for (uint32_t base = 0; base < n; base += 32) {
-                const uint32_t i = base + lane;
-                const bool valid = i < n;
-                uint32_t pos = 0, hh = 0xFFFFFFFFu, ff = 0, oldv = 0, fl = 0;
-                if (valid) {
-                    const uint2 d = S.rec[lst[i]];
-                    hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & R_POS; fl = d.y; oldv = d.y >> 16;
-                }
-                int best = -1; uint32_t bestf = 0; bool later = false;
-                #pragma unroll 1
-                for (uint32_t k = 0; k < n; ++k) {
-                    const uint2 dk = S.rec[lst[k]];      // broadcast reads
-                    const uint32_t pk = dk.y & R_POS;
-                    if ((dk.x & 0xFFFFu) == hh) {
-                        if (pk < pos && (int)pk > best) { best = (int)pk; bestf = dk.x >> 16; }
-                        later |= pk > pos;
-                    }
-                }
-                const bool touched = (fl & R_TOUCHED) != 0;
-                const bool hit = valid && (best >= 0 ? (bestf == ff) : (touched && oldv == ff));
-                if (hit) atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
-                if (valid && !later) {
-                    S.tab[hh] = (uint16_t)ff;
-                    if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
-                }
-                if (valid && (fl & R_MISSER)) S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
-                append_unres_class(S, warp, valid && best < 0 && !touched, run_q0 + pos, hh, ff, unres_run);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) S.cls_count[warp] = 0;
-    }
-    DNS_PH(6)
-    __syncthreads();  // S4: dictionary final for this tile, sigw[buf] final
-    DNS_PH(7)
-}
-
-// run r owns the flag-pass tiles [run_tile_begin(r), run_tile_begin(r + 1)); `tiles64` = number of 64-block tiles of the stream
-__host__ __device__ __forceinline__ uint32_t flag_tiles(uint32_t tiles64) { return (tiles64 + 1) / 2; }
-__host__ __device__ __forceinline__ uint64_t run_tile_begin(uint32_t r, uint32_t nruns, uint32_t tiles64) { return (uint64_t)r * flag_tiles(tiles64) / nruns; }
 
 __global__ void __launch_bounds__(FP_THREADS, 1)
-cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_total /* 64-block tiles */, uint32_t nruns,
+cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_total, uint32_t nruns,
                uint32_t* __restrict__ sigw_g,        // 2 x u32 per block (low half first)
-               uint2* __restrict__ unres,            // nruns x 32 sublists x 2048
-               uint32_t* __restrict__ unres_count,   // nruns x 32
+               uint2* __restrict__ unres,            // nruns x 65536
+               uint32_t* __restrict__ unres_count,   // nruns
                uint32_t* __restrict__ final_tab,     // nruns x 65536: touched << 16 | fp
                const uint8_t* __restrict__ copymap,  // optional: 1 byte per block, non-zero = copy-mode block (skipped)
                const Status* __restrict__ gate)      // optional: run only while the protection iteration is still open
@@ -346,10 +129,10 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
     FlagSmem& S = *reinterpret_cast<FlagSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t run = blockIdx.x;
-    const uint64_t t_begin = run_tile_begin(run, nruns, tiles_total);
-    const uint64_t t_end = run_tile_begin(run + 1, nruns, tiles_total);
+    const uint64_t t_begin = (uint64_t)run * tiles_total / nruns;
+    const uint64_t t_end = (uint64_t)(run + 1) * tiles_total / nruns;
     uint2* __restrict__ unres_run = unres + (size_t)run * 65536;
-    const uint32_t pos0 = warp * WARP_Q + lane;  // position of my sub-row 0 quad inside a tile; sub-row j adds 32*j
+    const uint32_t pos0 = warp * 128 + lane;  // position of my sub-row 0 quad inside a tile; sub-row j adds 32*j
     // run-relative 32-bit geometry (a run is < 2^32 quads): keeps 64-bit compares out of the tile loop
     const uint32_t ntile_run = (uint32_t)(t_end - t_begin);
     const uint64_t q_begin = t_begin * TILE_Q;
@@ -357,7 +140,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
     const uint32_t run_quads = q_begin < q_end64 ? (uint32_t)(q_end64 - q_begin) : 0u;
     const uint32_t* __restrict__ rin = in + q_begin;
     uint32_t* __restrict__ rsig = sigw_g + t_begin * (TILE_Q / 32);
-    const uint8_t* __restrict__ rcm = copymap ? copymap + t_begin * (TILE_Q / 64) : nullptr;
+    const uint8_t* __restrict__ rcm = copymap ? copymap + t_begin * 64 : nullptr;
 
     // ---- init shared state -------------------------------------------------------------------------
     {
@@ -366,11 +149,11 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         #pragma unroll 1
         for (uint32_t i = tid; i < 65536 * 2 / 16; i += FP_THREADS) t4[i] = z;
         #pragma unroll 1
-        for (uint32_t i = tid; i < 2048; i += FP_THREADS) S.vbit[i] = 0;
+        for (uint32_t i = tid; i < 2048; i += FP_THREADS) { S.vbit[i] = 0; S.conf[i] = 0; }
         #pragma unroll 1
         for (uint32_t i = tid; i < SIDE_N; i += FP_THREADS) S.side[i] = SIDE_EMPTY;
-        if (tid < CLS_N) { S.cls_count[tid] = 0; S.unres_cnt[tid] = 0; }
-        if (tid == 0) S.cls_overflow = 0;
+        if (tid < CLS_N) S.cls_count[tid] = 0;
+        if (tid == 0) { S.unres_count = 0; S.cls_overflow = 0; S.nrec = 0; }
     }
     __syncthreads();
 
@@ -381,40 +164,224 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 
 #ifdef DNS_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define DNS_PH(k) { long long tn = clock64(); ph[k] += tn - tprev; tprev = tn; }
+#else
+#define DNS_PH(k)
 #endif
     #pragma unroll 1
     for (uint32_t lt = 0; lt < ntile_run; ++lt) {
-        uint32_t q[FP_QPT];
+        uint32_t q[FP_QPT], h[FP_QPT], f[FP_QPT];
         const uint32_t run_q0 = lt * TILE_Q;                                  // first quad of the tile, relative to the run
         const uint32_t left = run_q0 < run_quads ? run_quads - run_q0 : 0u;   // quads left in the run from here
         const uint32_t rem = left < (uint32_t)TILE_Q ? left : (uint32_t)TILE_Q;
 #pragma unroll
         for (int j = 0; j < FP_QPT; ++j) q[j] = nxt[j];
-        if (left >= 2u * TILE_Q) {   // prefetch the next tile (register double buffer; consumed one full tile later)
-            const uint32_t* __restrict__ np = rin + run_q0 + TILE_Q + pos0;
-#pragma unroll
-            for (int j = 0; j < FP_QPT; ++j) nxt[j] = ld_stream_u32(np + 32 * j);
-        } else {
+        {   // prefetch next tile (register double buffer; consumed one full tile later)
             const uint32_t nleft = left > (uint32_t)TILE_Q ? left - TILE_Q : 0u;
             const uint32_t* __restrict__ np = rin + run_q0 + TILE_Q + pos0;
 #pragma unroll
             for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nleft) ? ld_stream_u32(np + 32 * j) : 0u;
         }
-        // the previous tile's flag words leave for HBM while this tile is being worked on (workspace is sized in whole tiles)
-        if (lt > 0 && tid < TILE_Q / 32) rsig[(lt - 1) * (TILE_Q / 32) + tid] = S.sigw[(lt - 1) & 1][tid];
 
-        const int buf = (int)(lt & 1);
-        if (rcm != nullptr || rem < (uint32_t)TILE_Q) flag_tile<true>(S, q, rin + run_q0, rem, run_q0, buf, unres_run, rcm ? rcm + lt * (TILE_Q / 64) : nullptr DNS_PH_PASS);
-        else flag_tile<false>(S, q, rin + run_q0, rem, run_q0, buf, unres_run, nullptr DNS_PH_PASS);
+        uint32_t actmask = 0;     // bit j: my sub-row j quad exists and its block is not in copy mode
+        {
+            uint32_t cp = 0;      // bit 0/1: block 2*warp / 2*warp+1 of this tile is a copy-mode block
+            if (rcm) cp = (rcm[lt * 64 + warp * 2] ? 1u : 0u) | (rcm[lt * 64 + warp * 2 + 1] ? 2u : 0u);
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j)
+                if (pos0 + 32 * j < rem && !((cp >> (j >> 1)) & 1u)) actmask |= 1u << j;
+        }
+        // ---- phase A: read the pre-tile dictionary; compact the missers into S.rec --------------------
+        uint32_t missmask = 0;    // bit j: my sub-row j quad missed
+        {
+            uint32_t old[FP_QPT], tch = 0;
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j) {
+                const uint32_t p = hash_prod(q[j]);
+                h[j] = prod_hash(p);
+                f[j] = prod_fp(p, q[j]);
+                old[j] = S.tab[h[j]];
+            }
+            uint32_t mb[FP_QPT], tot = 0;
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j) {
+                bool touched = old[j] != 0;
+                if (!touched) touched = bit_test(S.vbit, h[j]);
+                if (touched) tch |= 1u << j;
+                const bool miss = ((actmask >> j) & 1u) && !(touched && old[j] == f[j]);
+                if (miss) missmask |= 1u << j;
+                mb[j] = __ballot_sync(0xFFFFFFFFu, miss);
+                tot += __popc(mb[j]);
+            }
+            if (tot) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&S.nrec, tot);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+                for (int j = 0; j < FP_QPT; ++j) {
+                    if (missmask & (1u << j))
+                        S.rec[base + __popc(mb[j] & lanemask_lt())] =
+                            make_uint2(h[j] | (f[j] << 16), (pos0 + 32 * j) | ((tch >> j) & 1u ? R_TOUCHED : 0u) | (old[j] << 16));
+                    base += __popc(mb[j]);
+                }
+            }
+        }
+        __syncthreads();  // S1: all reads of tab/vbit precede the publishes; S.nrec = number of missers
+        DNS_PH(0)
+        const uint32_t nmiss = S.nrec;  // stable until phase C appends behind it
+
+        // ---- phase B: missers publish ---------------------------------------------------------------
+        #pragma unroll 1
+        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+            const uint2 r = S.rec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            S.tab[hh] = (uint16_t)(r.x >> 16);  // racy between different values on purpose
+            atomicMin(&S.side[hh & (SIDE_N - 1)], ((r.y & 0xFFFu) << 16) | hh);
+        }
+        __syncthreads();  // S2
+        DNS_PH(1)
+
+        // ---- phase C: read back ----------------------------------------------------------------------
+        // hit members: the bucket still holds my value unless some misser published (its value differs from mine)
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) {
+            const uint32_t pos = pos0 + 32 * j;
+            bool ok = false;
+            if (((actmask >> j) & 1u) && !(missmask & (1u << j))) {
+                ok = S.tab[h[j]] == f[j];
+                if (!ok) {
+                    const uint32_t slot = S.side[h[j] & (SIDE_N - 1)];
+                    if ((slot & 0xFFFFu) == h[j] && pos < (slot >> 16)) {
+                        ok = true;  // every misser of my bucket comes after me
+                    } else {
+                        // slow hit member: join the records and my class list, raise the conflict bit
+                        const uint32_t idx = atomicAdd(&S.nrec, 1u);
+                        S.rec[idx] = make_uint2(h[j] | (f[j] << 16), pos | R_TOUCHED | (f[j] << 16));
+                        const uint32_t c = h[j] >> 11;
+                        const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
+                        if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)idx; else S.cls_overflow = 1;
+                        atomicOr(&S.conf[h[j] >> 5], 1u << (h[j] & 31));
+                    }
+                }
+            }
+            const uint32_t fb = __ballot_sync(0xFFFFFFFFu, ok);
+            if (lane == 0) S.sigw[warp * 4 + j] = fb;
+        }
+        // missers: do all missers of my bucket agree, and who is first?
+        #pragma unroll 1
+        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+            const uint2 r = S.rec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            const uint32_t slot = S.side[hh & (SIDE_N - 1)];
+            const uint32_t w = S.tab[hh];
+            uint32_t y = r.y;
+            if ((slot & 0xFFFFu) != hh || w != (r.x >> 16)) {   // foreign slot owner, or missers disagree
+                y |= R_SLOW;
+                atomicOr(&S.conf[hh >> 5], 1u << (hh & 31));
+            } else if (slot == (((r.y & 0xFFFu) << 16) | hh)) {
+                y |= R_FIRST;
+            }
+            if (y != r.y) S.rec[i].y = y;
+        }
+        __syncthreads();  // S3
+        DNS_PH(2)
+
+        // ---- phase D: missers classify ----------------------------------------------------------------
+        #pragma unroll 1
+        for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+            const uint2 r = S.rec[i];
+            const uint32_t hh = r.x & 0xFFFFu;
+            uint32_t y = r.y;
+            if (!(y & R_SLOW) && bit_test(S.conf, hh)) { y |= R_SLOW; S.rec[i].y = y; }
+            if (y & R_SLOW) {
+                const uint32_t c = hh >> 11;
+                const uint32_t k = atomicAdd(&S.cls_count[c], 1u);
+                if (k < CLS_CAP) S.cls_list[c][k] = (uint16_t)i; else S.cls_overflow = 1;
+            } else if (!(y & R_FIRST)) {
+                const uint32_t pos = y & 0xFFFu;
+                atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));  // predecessor in the bucket is a misser with my value
+            }
+            S.side[hh & (SIDE_N - 1)] = SIDE_EMPTY;
+        }
+        __syncthreads();  // S4
+        DNS_PH(3)
+
+        // ---- phase F ------------------------------------------------------------------------------------
+        S.conf[tid] = 0; S.conf[tid + FP_THREADS] = 0;   // all readers of the conflict bits are behind S4; next set in the next tile's phase C
+        if (S.cls_overflow) {
+            // restore the pre-tile dictionary (only missers wrote), clear the per-tile state, walk the tile in order
+            #pragma unroll 1
+            for (uint32_t i = tid; i < nmiss; i += FP_THREADS) {
+                const uint2 r = S.rec[i];
+                S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
+            }
+            if (tid < CLS_N) S.cls_count[tid] = 0;
+            __syncthreads();
+            uint32_t* qs = reinterpret_cast<uint32_t*>(S.rec);
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j) qs[pos0 + 32 * j] = q[j];
+            if (tid == 0) { S.nrec = 0; S.cls_overflow = 0; }
+            __syncthreads();
+            if (warp == 0) tile_in_order(S, qs, rem, run_q0, unres_run, rcm ? rcm + lt * 64 : nullptr);
+        } else {
+            // first missers of agreeing buckets: genuine miss or unresolved first touch; deferred vbit; conflict-bit cleanup
+            #pragma unroll 1
+            for (uint32_t base = warp * 32; base < nmiss; base += FP_THREADS) {
+                const uint32_t i = base + lane;
+                uint2 r = make_uint2(0, 0);
+                if (i < nmiss) r = S.rec[i];
+                const uint32_t hh = r.x & 0xFFFFu;
+                const bool first = (i < nmiss) && (r.y & (R_FIRST | R_SLOW)) == R_FIRST;
+                if (first && (r.x >> 16) == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                append_unres(first && !(r.y & R_TOUCHED), run_q0 + (r.y & 0xFFFu), hh, r.x >> 16, &S.unres_count, unres_run);
+            }
+            // slow members, warp w <- class w. In-order semantics per bucket: my predecessor is the member of my bucket
+            // with the largest smaller position; without one the pre-tile value decides. The last member's value stays.
+            const uint32_t n = S.cls_count[warp];
+            const uint16_t* __restrict__ lst = S.cls_list[warp];
+            #pragma unroll 1
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < n;
+                uint32_t pos = 0, hh = 0xFFFFFFFFu, ff = 0, oldv = 0; bool touched = false;
+                if (valid) {
+                    const uint2 d = S.rec[lst[i]];
+                    hh = d.x & 0xFFFFu; ff = d.x >> 16; pos = d.y & 0xFFFu; touched = (d.y & R_TOUCHED) != 0; oldv = d.y >> 16;
+                }
+                int best = -1; uint32_t bestf = 0; bool later = false;
+                #pragma unroll 1
+                for (uint32_t k = 0; k < n; ++k) {
+                    const uint2 dk = S.rec[lst[k]];      // broadcast reads
+                    const uint32_t pk = dk.y & 0xFFFu;
+                    if ((dk.x & 0xFFFFu) == hh) {
+                        if (pk < pos && (int)pk > best) { best = (int)pk; bestf = dk.x >> 16; }
+                        later |= pk > pos;
+                    }
+                }
+                const bool hit = valid && (best >= 0 ? (bestf == ff) : (touched && oldv == ff));
+                if (hit) atomicOr(&S.sigw[pos >> 5], 1u << (pos & 31));
+                if (valid && !later) {
+                    S.tab[hh] = (uint16_t)ff;
+                    if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                }
+                append_unres(valid && best < 0 && !touched, run_q0 + pos, hh, ff, &S.unres_count, unres_run);
+            }
+            __syncwarp();
+            if (lane == 0) S.cls_count[warp] = 0;
+            if (tid == 0) S.nrec = 0;
+        }
+        __syncthreads();  // S5: dictionary final for this tile, sigw final
+        DNS_PH(4)
+
+        if (tid < TILE_Q / 32) rsig[lt * (TILE_Q / 32) + tid] = S.sigw[tid];  // workspace is sized in whole tiles
+        // (the next iteration rewrites S.sigw only after two more barriers)
     }
-    if (ntile_run > 0 && tid < TILE_Q / 32) rsig[(ntile_run - 1) * (TILE_Q / 32) + tid] = S.sigw[(ntile_run - 1) & 1][tid];
-#ifdef DNS_PHASE_TIMING
-    if (run == 77 && (tid == 0 || tid == 32 * 17 + 5) && ntile_run) { const long long nt = (long long)ntile_run;
-        printf("run %u tid %u tiles %lld cycles/tile: A %lld |S1 %lld| B %lld |S2 %lld| C %lld |S3 %lld| F %lld |S4+loop top %lld|  total %lld\n", run, tid, nt,
-               ph[0] / nt, ph[1] / nt, ph[2] / nt, ph[3] / nt, ph[4] / nt, ph[5] / nt, ph[6] / nt, ph[7] / nt,
-               (ph[0] + ph[1] + ph[2] + ph[3] + ph[4] + ph[5] + ph[6] + ph[7]) / nt); }
-#endif
 
+#ifdef DNS_PHASE_TIMING
+    if (tid == 0 && run == 77) { const long long nt = (long long)ntile_run;
+        printf("run %u tiles %lld cycles/tile: A %lld B %lld C %lld D %lld F %lld  total %lld\n", run, nt,
+               ph[0] / nt, ph[1] / nt, ph[2] / nt, ph[3] / nt, ph[4] / nt, (ph[0] + ph[1] + ph[2] + ph[3] + ph[4]) / nt); }
+#endif
     // ---- export the run's last-writer table ---------------------------------------------------------
     #pragma unroll 1
     for (uint32_t i = tid; i < 65536; i += FP_THREADS) {
@@ -422,7 +389,7 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
         uint32_t tch = (v != 0 || bit_test(S.vbit, i)) ? 0x10000u : 0u;
         final_tab[(size_t)run * 65536 + i] = v | tch;
     }
-    if (tid < CLS_N) unres_count[run * CLS_N + tid] = S.unres_cnt[tid] < (uint32_t)UNRES_PER_CLASS ? S.unres_cnt[tid] : (uint32_t)UNRES_PER_CLASS;
+    if (tid == 0) unres_count[run] = S.unres_count < 65536u ? S.unres_count : 65536u;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -450,15 +417,14 @@ __global__ void cham_resolve(const uint2* __restrict__ unres, const uint32_t* __
                              const uint32_t* __restrict__ carry, uint32_t tiles_total, uint32_t nruns,
                              uint32_t* __restrict__ sigw_g, const Status* __restrict__ gate = nullptr) {
     if (!gate_open(gate)) return;
-    const uint32_t run = blockIdx.y, cls = blockIdx.x;            // one block per (run, class sublist)
-    const uint32_t n = unres_count[run * CLS_N + cls];
-    const uint64_t run_q0 = run_tile_begin(run, nruns, tiles_total) * TILE_Q;
-    const uint2* __restrict__ lst = unres + (size_t)run * 65536 + (size_t)cls * UNRES_PER_CLASS;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint2 e = lst[i];
-        const uint32_t c = carry[(size_t)run * 65536 + (e.y & 0xFFFFu)];
+    const uint32_t run = blockIdx.y;
+    const uint32_t n = unres_count[run];
+    const uint64_t run_q0 = ((uint64_t)run * tiles_total / nruns) * TILE_Q;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint2 e = unres[(size_t)run * 65536 + i];
+        uint32_t c = carry[(size_t)run * 65536 + (e.y & 0xFFFFu)];
         if ((c & 0x10000u) && (c & 0xFFFFu) == (e.y >> 16)) {
-            const uint64_t gq = run_q0 + e.x;
+            uint64_t gq = run_q0 + e.x;
             atomicOr(&sigw_g[gq >> 5], 1u << (gq & 31));
         }
     }
@@ -1064,7 +1030,7 @@ size_t cham_workspace_bytes(size_t nbytes, int nruns_max, ChamLayout* L) {
     L->group_total = take((ngroups + 1) * sizeof(uint64_t));
     L->group_off = take((ngroups + 1) * sizeof(uint64_t));
     L->unres = take((size_t)nruns_max * 65536 * sizeof(uint2));
-    L->unres_count = take((size_t)nruns_max * CLS_N * sizeof(uint32_t));
+    L->unres_count = take((size_t)nruns_max * sizeof(uint32_t));
     L->final_tab = take((size_t)nruns_max * 65536 * sizeof(uint32_t));
     L->carry = take((size_t)nruns_max * 65536 * sizeof(uint32_t));
     L->total = off;
@@ -1144,7 +1110,7 @@ cudaError_t cham_phase2_begin(const uint8_t* d_in, size_t nbytes, uint8_t* ws, c
     uint32_t* sigw = reinterpret_cast<uint32_t*>(ws + L.sigw);
     cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
                                                     reinterpret_cast<uint32_t*>(ws + L.carry), nullptr);
-    cham_resolve<<<dim3(CLS_N, nruns), 128, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+    cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
                                                      reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw);
     cham_tile_sizes<<<(ntiles + 7) / 8, 256, 0, stream>>>(sigw, nullptr, nbytes, nblocks, ntiles, 0, 1, assume_prev_inc ? 1 : 0, st,
                                                           reinterpret_cast<uint32_t*>(ws + L.tile_bytes));
@@ -1179,7 +1145,7 @@ cudaError_t cham_phase2_rounds(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
                 reinterpret_cast<uint32_t*>(ws + L.final_tab), copymap, st);
             cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,
                                                             reinterpret_cast<uint32_t*>(ws + L.carry), nullptr, st);
-            cham_resolve<<<dim3(CLS_N, nruns), 128, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
+            cham_resolve<<<dim3(32, nruns), 256, 0, stream>>>(reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
                                                              reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw, st);
             *launches += 3;
         }

@@ -23,6 +23,7 @@
 //
 // Lion is NOT decoded here: its 5-deep move-to-front lists make the same iteration advance one run per round (a misplaced
 // operation desynchronises a whole list; measured in tests/cl_model.cpp), so lion_decode stays on the in-order kernel.
+#include <stdlib.h>
 #include "common.cuh"
 #include "encode_internal.cuh"
 #include "decode_bounds.cuh"
@@ -39,7 +40,7 @@ using namespace cld;
 
 constexpr uint32_t CTX_PASS = 0xFFFFFFFEu;        // ctx_out of a run without encoded quads
 constexpr int RP_WARPS = 4;                       // warps (runs) per CTA of the walk kernels
-constexpr int MAX_ROUNDS = 24;
+constexpr int MAX_ROUNDS = 40;
 
 struct ClStatus {
     unsigned int changed, unknown, done, rounds;
@@ -179,10 +180,12 @@ __global__ void cd_cmap_resolve(const DecStatus* __restrict__ st, uint32_t nruns
 // context of the first encoded quad of every run when the stream says it: the nearest earlier encoded block ends with a quad that is
 // not predicted (its hash is in K); otherwise unknown until a round has produced it. last_hash starts as 0 (cheetah.rs:54).
 __global__ void cd_ctx_init(const DecStatus* __restrict__ st, uint32_t nruns, const uint4* __restrict__ flags, const uint16_t* __restrict__ K,
-                            uint32_t* __restrict__ ctx_in, ClStatus* __restrict__ cs) {
+                            uint32_t* __restrict__ ctx_in, uint32_t* __restrict__ dirty_cur, uint32_t* __restrict__ dirty_next, uint32_t* __restrict__ run_epoch,
+                            ClStatus* __restrict__ cs) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0) { cs->changed = 0; cs->unknown = 0; cs->done = st->error ? 1u : 0u; cs->rounds = 0; cs->final_ctx = 0; cs->gave_up = 0; }
+    if (r == 0) { cs->changed = 0; cs->unknown = 0; cs->done = st->error ? 1u : 0u; cs->rounds = 0; cs->final_ctx = 0; cs->gave_up = 0; cs->pad0 = 0; }
     if (r >= nruns || st->error) return;
+    dirty_cur[r] = 1; dirty_next[r] = 0; run_epoch[r] = 0;      // round 0 walks every run
     uint64_t s = run_step_begin(r, nruns, st->main_blocks);
     uint32_t c = 0;
     while (s > 0) {
@@ -200,11 +203,19 @@ __global__ void cd_ctx_init(const DecStatus* __restrict__ st, uint32_t nruns, co
 __global__ void __launch_bounds__(RP_WARPS * 32)
 cd_pred_walk(const DecStatus* __restrict__ st, ClStatus* __restrict__ cs, uint32_t nruns, uint32_t round, const uint4* __restrict__ flags,
              const uint16_t* __restrict__ K, uint2* __restrict__ entP_all, const uint32_t* __restrict__ snap_all, const uint32_t* __restrict__ ctx_in,
-             uint32_t* __restrict__ ctx_out, uint32_t* __restrict__ out) {
+             uint32_t* __restrict__ ctx_out, const uint32_t* __restrict__ dirty_cur, uint32_t* __restrict__ dirty_next, uint32_t* __restrict__ run_epoch,
+             uint32_t* __restrict__ rbits_all, uint32_t* __restrict__ out) {
     if (cs->done) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (r >= nruns) return;
+    // A run is walked again only if something it depends on changed: its entry context, or a snapshot entry it read (cd_pred_fold
+    // compares against the run's read set), or it met an unknown last time. Otherwise its values, its table entries (validated by
+    // run_epoch) and its exit context stand.
+    if (!dirty_cur[r]) return;
+    uint32_t* __restrict__ rbits = rbits_all + (size_t)r * 2048;
+    for (uint32_t i = lane; i < 2048; i += 32) rbits[i] = 0;
+    __syncwarp();
     const uint32_t epoch = round + 1;
     const bool has_snap = round > 0 || r == 0;
     const uint64_t nsteps = st->main_blocks;
@@ -250,8 +261,10 @@ cd_pred_walk(const DecStatus* __restrict__ st, ClStatus* __restrict__ cs, uint32
                     uint32_t mv = ee.x, me = meta_epoch(ee.y), ms = ss;
                     mv = __shfl_sync(0xFFFFFFFFu, mv, p); me = __shfl_sync(0xFFFFFFFFu, me, p); ms = __shfl_sync(0xFFFFFFFFu, ms, p);
                     if (me == epoch) val = mv;                      // written earlier in this run
-                    else if (has_snap) val = ms;                    // carried in (as of the previous round's fold)
-                    else unk = true;                                // round 0: nothing is known about what earlier runs left here
+                    else if (has_snap) {                            // carried in (as of the previous round's fold): remember that I depend on it
+                        val = ms;
+                        if ((int)lane == p) atomicOr(&rbits[c >> 5], 1u << (c & 31));
+                    } else unk = true;                              // round 0: nothing is known about what earlier runs left here
                 }
             }
             const uint32_t hp = unk ? H_UNKNOWN : hash16(val);      // cheetah.rs:101
@@ -277,54 +290,61 @@ cd_pred_walk(const DecStatus* __restrict__ st, ClStatus* __restrict__ cs, uint32
     }
     if (lane == 0) {
         ctx_out[r] = any_active ? carry : CTX_PASS;
-        if (unknown_seen) cs->unknown = 1;
+        run_epoch[r] = epoch;
+        if (unknown_seen) dirty_next[r] = 1;
     }
 }
 
-// one thread per context: snapshot of the table in front of every run, and the table after the main loop (for the tail)
+// one thread per context: snapshot of the table in front of every run (in place), and the table after the main loop (for the tail).
+// A run whose snapshot changed at a context it read has to be walked again.
 __global__ void cd_pred_fold(const DecStatus* __restrict__ st, ClStatus* __restrict__ cs, uint32_t nruns, uint32_t round, const uint2* __restrict__ entP_all,
-                             const uint32_t* __restrict__ snap_old, uint32_t* __restrict__ snap_new, uint32_t* __restrict__ pred_final) {
+                             uint32_t* __restrict__ snap, const uint32_t* __restrict__ run_epoch, const uint32_t* __restrict__ rbits_all,
+                             uint32_t* __restrict__ dirty_next, uint32_t* __restrict__ pred_final) {
     if (cs->done) return;
     const uint32_t ctx = blockIdx.x * blockDim.x + threadIdx.x;
     if (ctx >= 65536) return;
-    const uint32_t epoch = round + 1;
     uint32_t c = 0;                                                // prediction table starts as 0 everywhere (cheetah.rs:53)
-    bool changed = false;
     for (uint32_t r0 = 0; r0 < nruns; r0 += 8) {
-        uint2 e[8]; uint32_t so[8];
+        uint2 e[8]; uint32_t so[8], ep[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const bool ok = r0 + k < nruns;
             e[k] = ok ? entP_all[(size_t)(r0 + k) * 65536 + ctx] : make_uint2(0, 0);
-            so[k] = ok ? snap_old[(size_t)(r0 + k) * 65536 + ctx] : 0u;
+            so[k] = ok ? snap[(size_t)(r0 + k) * 65536 + ctx] : 0u;
+            ep[k] = ok ? run_epoch[r0 + k] : 0u;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (r0 + k >= nruns) break;
-            snap_new[(size_t)(r0 + k) * 65536 + ctx] = c;
-            if ((round > 0 || r0 + k == 0) && so[k] != c) changed = true;
-            if (meta_epoch(e[k].y) == epoch) c = e[k].x;
+            if (so[k] != c) {
+                snap[(size_t)(r0 + k) * 65536 + ctx] = c;
+                if (round > 0 && ((rbits_all[(size_t)(r0 + k) * 2048 + (ctx >> 5)] >> (ctx & 31)) & 1u)) dirty_next[r0 + k] = 1;
+            }
+            if (meta_epoch(e[k].y) == ep[k] && ep[k] != 0) c = e[k].x;
         }
     }
     pred_final[ctx] = c;
-    if (changed) cs->changed = 1;
     (void)st;
 }
 
 // context sweep + verdict of the round (one thread)
-__global__ void cd_round_end(ClStatus* __restrict__ cs, uint32_t nruns, uint32_t round, uint32_t* __restrict__ ctx_in, const uint32_t* __restrict__ ctx_out) {
+__global__ void cd_round_end(ClStatus* __restrict__ cs, uint32_t nruns, uint32_t round, uint32_t* __restrict__ ctx_in, const uint32_t* __restrict__ ctx_out,
+                             uint32_t* __restrict__ dirty_cur, uint32_t* __restrict__ dirty_next) {
     if (threadIdx.x || blockIdx.x || cs->done) return;
-    bool changed = cs->changed != 0 || (round == 0 && nruns > 1);
-    uint32_t c = 0;
+    uint32_t c = 0, ndirty = 0;
     for (uint32_t r = 0; r < nruns; ++r) {
-        if (ctx_in[r] != c) { changed = true; ctx_in[r] = c; }
+        uint32_t d = dirty_next[r];
+        if (round == 0 && r > 0) d = 1;                            // runs > 0 had no snapshot in round 0
+        if (ctx_in[r] != c) { d = 1; ctx_in[r] = c; }
+        dirty_cur[r] = d; dirty_next[r] = 0;
+        ndirty += d;
         const uint32_t o = ctx_out[r];
         if (o != CTX_PASS) c = o;
     }
     cs->final_ctx = c;
     cs->rounds = round + 1;
-    if (!changed && !cs->unknown) cs->done = 1;
-    cs->changed = 0; cs->unknown = 0;
+    cs->pad0 += ndirty;                                            // diagnostic: run walks queued after round 0
+    if (ndirty == 0) cs->done = 1;
 }
 
 // verdict for the caller: *d_fallback != 0 -> the in-order kernel (queued behind, gated on it) has to produce the result
@@ -339,14 +359,15 @@ __global__ void cd_finish(const DecStatus* __restrict__ st, ClStatus* __restrict
 
 using namespace cheedec;
 
-struct CheeDecLayout { bounds::BoundsLayout B; size_t cs, flags, K, usym, ctx_in, ctx_out, cin, snap0, snap1, total; };
+struct CheeDecLayout { bounds::BoundsLayout B; size_t cs, flags, K, usym, ctx_in, ctx_out, dirty, run_epoch, rbits, cin, snap0, total; };
 
 static uint32_t cd_pick_runs(size_t nbytes, int num_sms) {
     const uint64_t maxblocks = nbytes / 8 + 2;
     (void)maxblocks;
     // a run should decode to >= 64 KiB (512 blocks); the stream is at most 8.5 bytes per block... use the stream size as a proxy
     uint64_t r = nbytes / (48u << 10);
-    const uint64_t cap = (uint64_t)num_sms * 8;
+    static const int per_sm = [] { const char* v = getenv("DENSITY_B200_DEC_RUNS_PER_SM"); const int k = v ? atoi(v) : 0; return (k >= 1 && k <= 32) ? k : 8; }();
+    const uint64_t cap = (uint64_t)num_sms * per_sm;   // warps (runs) per SM: tuning knob, the result does not depend on it
     if (r > cap) r = cap;
     if (r < 1) r = 1;
     return (uint32_t)r;
@@ -362,9 +383,11 @@ static size_t cd_layout(size_t nbytes, size_t cap, uint32_t nruns, CheeDecLayout
     L->usym = take(mb * sizeof(uint2));
     L->ctx_in = take((size_t)nruns * 4 + 64);
     L->ctx_out = take((size_t)nruns * 4 + 64);
+    L->dirty = take((size_t)nruns * 8 + 64);
+    L->run_epoch = take((size_t)nruns * 4 + 64);
+    L->rbits = take((size_t)nruns * 2048 * sizeof(uint32_t));
     L->cin = take((size_t)nruns * 65536 * sizeof(uint2));
     L->snap0 = take((size_t)nruns * 65536 * sizeof(uint32_t));
-    L->snap1 = take((size_t)nruns * 65536 * sizeof(uint32_t));
     L->total = off;
     return off;
 }
@@ -391,7 +414,11 @@ cudaError_t chee_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     uint32_t* ctx_in = reinterpret_cast<uint32_t*>(ws + L.ctx_in);
     uint32_t* ctx_out = reinterpret_cast<uint32_t*>(ws + L.ctx_out);
     uint2* cin = reinterpret_cast<uint2*>(ws + L.cin);
-    uint32_t* snap[2] = {reinterpret_cast<uint32_t*>(ws + L.snap0), reinterpret_cast<uint32_t*>(ws + L.snap1)};
+    uint32_t* snap = reinterpret_cast<uint32_t*>(ws + L.snap0);
+    uint32_t* dirty_cur = reinterpret_cast<uint32_t*>(ws + L.dirty);
+    uint32_t* dirty_next = dirty_cur + nruns;
+    uint32_t* run_epoch = reinterpret_cast<uint32_t*>(ws + L.run_epoch);
+    uint32_t* rbits = reinterpret_cast<uint32_t*>(ws + L.rbits);
     uint4* entC = reinterpret_cast<uint4*>(tables);
     uint2* entP = reinterpret_cast<uint2*>(tables + (size_t)nruns * 65536 * sizeof(uint4));
     uint32_t* out32 = reinterpret_cast<uint32_t*>(d_out);
@@ -400,7 +427,7 @@ cudaError_t chee_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     uint32_t* chunk_b = chunk_a + 65536;
     uint32_t* pred_final = chunk_a + 2 * 65536;
     e = cudaMemsetAsync(tables, 0, chee_decode_tables_bytes(nbytes, num_sms), stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(snap[0], 0, (size_t)nruns * 65536 * sizeof(uint32_t), stream);   // run 0's snapshot: the zero table
+    if (e == cudaSuccess) e = cudaMemsetAsync(snap, 0, (size_t)nruns * 65536 * sizeof(uint32_t), stream);   // run 0's snapshot: the zero table
     if (e != cudaSuccess) return e;
     const int wide = num_sms * 8;
     const uint32_t run_ctas = (nruns + RP_WARPS - 1) / RP_WARPS;
@@ -408,12 +435,12 @@ cudaError_t chee_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     cd_cmap_walk<<<run_ctas, RP_WARPS * 32, 0, stream>>>(st, nruns, flags, K, entC, out32, usym);
     cd_cmap_fold<<<65536 / 128, 128, 0, stream>>>(st, nruns, entC, cin, chunk_a, chunk_b);
     cd_cmap_resolve<<<wide, 256, 0, stream>>>(st, nruns, usym, K, cin, out32);
-    cd_ctx_init<<<(nruns + 127) / 128, 128, 0, stream>>>(st, nruns, flags, K, ctx_in, cs);
+    cd_ctx_init<<<(nruns + 127) / 128, 128, 0, stream>>>(st, nruns, flags, K, ctx_in, dirty_cur, dirty_next, run_epoch, cs);
     *launches += 5;
     for (int round = 0; round < MAX_ROUNDS; ++round) {
-        cd_pred_walk<<<run_ctas, RP_WARPS * 32, 0, stream>>>(st, cs, nruns, (uint32_t)round, flags, K, entP, snap[round & 1], ctx_in, ctx_out, out32);
-        cd_pred_fold<<<65536 / 128, 128, 0, stream>>>(st, cs, nruns, (uint32_t)round, entP, snap[round & 1], snap[(round & 1) ^ 1], pred_final);
-        cd_round_end<<<1, 32, 0, stream>>>(cs, nruns, (uint32_t)round, ctx_in, ctx_out);
+        cd_pred_walk<<<run_ctas, RP_WARPS * 32, 0, stream>>>(st, cs, nruns, (uint32_t)round, flags, K, entP, snap, ctx_in, ctx_out, dirty_cur, dirty_next, run_epoch, rbits, out32);
+        cd_pred_fold<<<65536 / 128, 128, 0, stream>>>(st, cs, nruns, (uint32_t)round, entP, snap, run_epoch, rbits, dirty_next, pred_final);
+        cd_round_end<<<1, 32, 0, stream>>>(cs, nruns, (uint32_t)round, ctx_in, ctx_out, dirty_cur, dirty_next);
         *launches += 3;
     }
     cd_finish<<<1, 1, 0, stream>>>(st, cs, d_fallback, d_out_size);

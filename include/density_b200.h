@@ -101,7 +101,7 @@ DENSITY_B200_API int density_b200_encode_status(uint64_t* out6);
    in_order_boundaries != 0: the stream had copy-mode blocks (codec.rs:89-92) and the boundaries came from the in-order walk. */
 DENSITY_B200_API int density_b200_decode_status(uint64_t* out10);
 /* Diagnostic: the context iteration of the last run-parallel Cheetah decode on the current device (synchronises the device):
-   out4 = {rounds used, settled (0: the in-order kernel took over), last hash after the main loop, round budget}. */
+   out4 = {rounds used, settled (0: the in-order kernel took over), run walks after round 0, round budget}. */
 DENSITY_B200_API int density_b200_cheetah_decode_rounds(uint32_t* out4);
 /* Same contract for decode; `cap` must be >= the original length. */
 DENSITY_B200_API int density_b200_decode_device(int alg, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t cap,

@@ -115,14 +115,22 @@ size_t decode_impl(const uint8_t* in, size_t n, uint8_t* out, size_t cap, uint32
     uint32_t rounds = 0; bool converged = false;
     std::vector<uint32_t> final_list(65536 * NP, 0);
     uint32_t final_ctx = 0;
+    // A run is walked again only if something it depends on changed (its entry context, a snapshot entry it read, an unknown it met):
+    // per-run read sets, per-run epochs (an entry is part of the run's transfer function iff it carries the epoch of the run's LAST walk)
+    std::vector<uint8_t> dirty(nruns, 1), dirty_next(nruns, 0);
+    std::vector<uint32_t> run_epoch(nruns, 0);
+    std::vector<std::vector<uint8_t>> rset(nruns, std::vector<uint8_t>(65536, 0));
+    uint64_t walks = 0;
     for (uint32_t round = 0; round < max_rounds && !converged; ++round) {
         ++rounds;
         const uint32_t epoch = round + 1;
-        bool unknown_seen = false;
         for (uint32_t r = 0; r < nruns; ++r) {
+            if (!dirty[r]) continue;
+            ++walks;
+            std::fill(rset[r].begin(), rset[r].end(), 0);
             const bool has_snap = round > 0 || r == 0;
             uint32_t ctx = ctx_in[r];
-            bool any_active = false;
+            bool any_active = false, unknown_seen = false;
             for (uint64_t i = run_begin(r); i < run_begin(r + 1); ++i) {
                 if (!active[i]) continue;
                 any_active = true;
@@ -132,13 +140,17 @@ size_t decode_impl(const uint8_t* in, size_t n, uint8_t* out, size_t cap, uint32
                     ctx = H; continue;
                 }
                 Entry<NP>& e = pt[r][ctx];
-                if (e.epoch != epoch) { list_init<NP>(e.L, has_snap ? &snap[((size_t)r * 65536 + ctx) * NP] : nullptr); e.epoch = epoch; }
+                if (e.epoch != epoch) {
+                    list_init<NP>(e.L, has_snap ? &snap[((size_t)r * 65536 + ctx) * NP] : nullptr); e.epoch = epoch;
+                    if (NP > 1 || kind[i] == K_PRED) rset[r][ctx] = 1;      // the carried-in list matters (Cheetah: only to a reader)
+                }
                 if (kind[i] == K_PRED) {
                     const int k = depth[i];
                     const bool unk = (e.L.unk >> k) & 1u;
                     val[i] = e.L.v[k];
                     H = unk ? H_UNKNOWN : hash16(val[i]);
                     if (unk) unknown_seen = true;
+                    if (NP == 1 && e.L.slot_tag(0) != TAG_LIT) rset[r][ctx] = 1;
                     if (k) list_mtf<NP>(e.L, k);
                 } else {
                     list_push<NP>(e.L, val[i]);
@@ -147,37 +159,35 @@ size_t decode_impl(const uint8_t* in, size_t n, uint8_t* out, size_t cap, uint32
                 ctx = H;
             }
             ctx_out[r] = any_active ? ctx : 0xFFFFFFFEu;   // PASS: the run has no encoded quad
+            run_epoch[r] = epoch;
+            if (unknown_seen) dirty_next[r] = 1;
         }
-        // fold: new snapshots; changed?
-        bool changed = false;
+        // fold: snapshots in place; a run whose snapshot changed at a key it read is dirty
         for (uint32_t key = 0; key < 65536; ++key) {
             uint32_t c[NP]; for (int s = 0; s < NP; ++s) c[s] = 0;          // prediction tables start as zeros (cheetah.rs:53, lion.rs:70)
             for (uint32_t r = 0; r < nruns; ++r) {
-                uint32_t* sn = &snap_new[((size_t)r * 65536 + key) * NP];
-                const uint32_t* so = &snap[((size_t)r * 65536 + key) * NP];
-                for (int s = 0; s < NP; ++s) { if (sn[s] != c[s]) {} sn[s] = c[s]; if ((round > 0 || r == 0) && so[s] != c[s]) changed = true; }
-                if (pt[r][key].epoch == epoch) list_carry<NP>(c, pt[r][key].L);
+                uint32_t* sn = &snap[((size_t)r * 65536 + key) * NP];
+                bool ch = false;
+                for (int s = 0; s < NP; ++s) { if (sn[s] != c[s]) { sn[s] = c[s]; ch = true; } }
+                if (ch && round > 0 && rset[r][key]) dirty_next[r] = 1;
+                if (pt[r][key].epoch == run_epoch[r] && run_epoch[r] != 0) list_carry<NP>(c, pt[r][key].L);
             }
             for (int s = 0; s < NP; ++s) final_list[key * NP + s] = c[s];
         }
-        if (round == 0 && nruns > 1) changed = true;       // runs > 0 had no snapshot in round 0
-        snap.swap(snap_new);
-        // context sweep
-        uint32_t c = 0;
+        // context sweep + verdict
+        uint32_t c = 0, ndirty = 0;
         for (uint32_t r = 0; r < nruns; ++r) {
-            if (ctx_in[r] != c) { changed = true; ctx_in[r] = c; }
-            if (c == H_UNKNOWN) {}   // stays unknown through PASS runs
+            uint8_t d = dirty_next[r];
+            if (round == 0 && r > 0) d = 1;                // runs > 0 had no snapshot in round 0
+            if (ctx_in[r] != c) { d = 1; ctx_in[r] = c; }
+            dirty[r] = d; dirty_next[r] = 0; ndirty += d;
             if (ctx_out[r] != 0xFFFFFFFEu) c = ctx_out[r];
         }
         final_ctx = c;
-        converged = !changed && !unknown_seen;
-        if (getenv("CL_MODEL_TRUTH")) {   // debug: truth = original quads
-            const uint32_t* truth = (const uint32_t*)strtoull(getenv("CL_MODEL_TRUTH"), 0, 10);
-            uint32_t bad_runs = 0; uint64_t bad = 0; int first_bad = -1;
-            for (uint32_t r = 0; r < nruns; ++r) { uint64_t b = 0; for (uint64_t i = run_begin(r); i < run_begin(r + 1) && i < nq; ++i) if (active[i] && kind[i] == K_PRED && val[i] != truth[i]) ++b; if (b) { ++bad_runs; if (first_bad < 0) first_bad = (int)r; } bad += b; }
-            fprintf(stderr, "round %u: wrong predicted values %llu in %u runs (first bad run %d) unknown_seen %d\n", round, (unsigned long long)bad, bad_runs, first_bad, (int)unknown_seen);
-        }
+        converged = ndirty == 0;
+        if (getenv("CL_MODEL_TRUTH")) fprintf(stderr, "round %u: dirty runs for the next round %u\n", round, ndirty);
     }
+    if (stats) stats[3] = (uint32_t)walks;
     if (stats) { stats[0] = rounds; stats[1] = converged; stats[2] = (uint32_t)nb; }
     if (!converged) return 0;
     // ---- write the main part --------------------------------------------------------------------------------------------------------

@@ -393,6 +393,349 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Pass 1, second formulation: write -> verify -> resolve the dirty members through a per-tile mailbox.
+//
+// Same contract as cham_flag_pass (inputs, outputs, unresolved list, last-writer table). Per 4096-quad tile:
+//   A  every quad reads the pre-tile dictionary: old != f => misser. A quad equal to the quad right before it in the stream is a hit
+//      whatever the dictionary holds (its predecessor in the bucket is that quad) and changes nothing: it is left out of everything
+//      below, so a run of equal quads costs one dictionary access.                                                       (barrier)
+//   B  missers store their fingerprint (racy on purpose).                                                              (barrier)
+//   C  hit members read again: unchanged => no misser in my bucket => flag 1, final. Everything else -- the missers and the hit
+//      members of a bucket some misser wrote to -- is a *dirty member* (~10 % of the quads on text). Each warp compacts its dirty
+//      members in stream order into its record region (ballot + popc) and then, one record per lane, drops the record's index into the
+//      mailbox of its bucket: 4096 slots (low 12 hash bits) x 4 entries of 16 bits (high 4 hash bits | record index).      (barrier)
+//   D  one record per lane again: the slot's entries with my bucket give my predecessor (largest smaller index: region order is
+//      stream order) => flag = predecessor's fingerprint == mine, or the pre-tile value when there is none; the member without a
+//      successor stores the bucket's final fingerprint. First touches of a bucket inside the run go to the unresolved list.  (barrier)
+// Clean buckets are never written and every dirty bucket is written once in D, so the dictionary after D is the sequential one.
+// Phases A-D do the same work in every warp whatever the data; a slot that would need a fifth entry (five dirty members of one
+// bucket, or of buckets sharing 12 hash bits, inside one tile) sends the tile to f6_replay: the in-order replay of the dirty
+// members by one warp (exact for any input, slow).
+// ------------------------------------------------------------------------------------------------------
+constexpr int F6_THREADS = 1024;
+constexpr int F6_MB_SLOTS = 4096, F6_MB_CAP = 4;      // mailboxes: slot = low 12 hash bits
+constexpr int F6_SEC_SLOTS = 64, F6_SEC_CAP = 16;      // overflow mailboxes shared by the slots with the same low 6 bits
+#ifdef DNS_PHASE_TIMING
+__device__ long long g_f6_ph[8];
+#define F6_PH(k) { if (threadIdx.x == 0 && blockIdx.x == 77) { long long tn = clock64(); g_f6_ph[k] += tn - f6_tprev; f6_tprev = tn; } }
+#define F6_PH_DECL long long f6_tprev = clock64();
+#else
+#define F6_PH(k)
+#define F6_PH_DECL
+#endif
+constexpr uint32_t F6_TOUCHED = 1u << 12, F6_DROPPED = 1u << 13;   // record.y: pos (12) | touched << 12 | dropped << 13 | pre-tile fingerprint << 16
+struct Flag6Smem {
+    uint16_t tab[65536];          // fingerprint of the last quad seen in each bucket
+    uint32_t vbit[2048];          // "bucket touched" for the one case tab cannot express (fingerprint 0)
+    uint2 rec[TILE_Q];            // warp w: records [128 w, 128 w + cnt[w]) in stream order. x = hash | fp << 16, y see above
+    union {
+        uint16_t mb[F6_MB_SLOTS][F6_MB_CAP];
+        uint2 dense[TILE_Q];      // fallback only (the mailboxes are void then): the same records, dense
+    };
+    uint32_t mbcnt[2][F6_MB_SLOTS / 4];   // entry counts, 8 bits per slot; double buffered (the idle half is cleared during the tile)
+    uint32_t sec[F6_SEC_SLOTS][F6_SEC_CAP];
+    uint32_t seccnt[2][F6_SEC_SLOTS];
+    uint32_t sigw[2][TILE_Q / 32];
+    uint32_t cnt[32];
+    uint32_t unres_count;
+    uint32_t overflow;
+};
+static_assert(sizeof(Flag6Smem) <= 227 * 1024, "flag pass shared memory");
+
+// Append the lanes with `pred` set to the run's unresolved list (warp-aggregated; all 32 lanes call).
+__device__ __forceinline__ void f6_append_unres(bool pred, uint32_t qidx_in_run, uint32_t hf, uint32_t* s_count, uint2* __restrict__ unres_run) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (m == 0) return;
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(s_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (pred) {
+        const uint32_t idx = base + __popc(m & lanemask_lt());
+        if (idx < 65536u) unres_run[idx] = make_uint2(qidx_in_run, hf);
+    }
+}
+
+// Fallback: in-order replay of the tile's dirty members by one warp. Copies the regions into one dense, stream-ordered list and
+// restores the pre-tile value of every dirty bucket (each record carries it), then walks the list 32 records per step
+// (match_any for records of the same bucket inside a step).
+__device__ __noinline__ void f6_replay(Flag6Smem& S, uint32_t buf, uint32_t run_q0, uint2* __restrict__ unres_run) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t c = S.cnt[lane];
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+    const uint32_t excl = incl - c;
+    const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    #pragma unroll 1
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint32_t w = 0;     // number of regions that end at or before i == the region that holds dense index i
+#pragma unroll
+        for (int b = 16; b >= 1; b >>= 1) { const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (w + b - 1) & 31); if (t <= i) w += b; }
+        const uint32_t e = __shfl_sync(0xFFFFFFFFu, excl, w & 31);
+        if (i < n) {
+            const uint2 r = S.rec[w * 128 + (i - e)];
+            S.dense[i] = r;
+            S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
+        }
+    }
+    __syncwarp();
+    #pragma unroll 1
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n;
+        uint2 r = make_uint2(0, 0);
+        if (valid) r = S.dense[i];
+        const uint32_t hh = r.x & 0xFFFFu, ff = r.x >> 16, pos = r.y & 0xFFFu;
+        uint32_t cur = 0;
+        if (valid) cur = S.tab[hh];
+        const uint32_t grp = __match_any_sync(0xFFFFFFFFu, valid ? hh : 0x10000u + lane);
+        const uint32_t lower = grp & lanemask_lt();
+        const uint32_t fprev = __shfl_sync(0xFFFFFFFFu, ff, lower ? 31 - __clz(lower) : 0);
+        bool touched = true, hit;
+        if (lower) hit = fprev == ff;
+        else {
+            if (cur == 0) touched = bit_test(S.vbit, hh);
+            hit = touched && cur == ff;
+        }
+        if (valid && (grp & lanemask_gt()) == 0) {
+            S.tab[hh] = (uint16_t)ff;
+            if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+        }
+        if (valid && hit) atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
+        f6_append_unres(valid && !touched, run_q0 + pos, r.x, &S.unres_count, unres_run);
+        __syncwarp();
+    }
+}
+
+// One tile. GENERIC: the tile is partial or has copy-mode blocks (`validmask` bit j: my sub-row j quad takes part).
+template <bool GENERIC>
+__device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[FP_QPT], uint32_t validmask, uint32_t buf, uint32_t run_q0,
+                                        uint2* __restrict__ unres_run) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t pos0 = warp * 128 + lane;
+    uint32_t h[FP_QPT], f[FP_QPT], old[FP_QPT];
+    uint32_t missmask = 0;
+    F6_PH_DECL
+    S.mbcnt[buf ^ 1u][tid] = 0;      // the other half of the mailbox counters: last read before the previous tile's final barrier
+    if (tid < F6_SEC_SLOTS) S.seccnt[buf ^ 1u][tid] = 0;
+    // ---- A
+#pragma unroll
+    for (int j = 0; j < FP_QPT; ++j) {
+        const uint32_t p = hash_prod(q[j]);
+        h[j] = prod_hash(p);
+        f[j] = prod_fp(p, q[j]);
+        old[j] = S.tab[h[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < FP_QPT; ++j) {
+        bool miss = old[j] != f[j];
+        if (f[j] == 0 && old[j] == 0) miss = !bit_test(S.vbit, h[j]);   // fingerprint 0 is also what an untouched bucket shows
+        if (GENERIC) miss = miss && ((validmask >> j) & 1u);
+        if (miss) missmask |= 1u << j;
+    }
+    __syncthreads();   // S1: every read of the pre-tile dictionary precedes the publishes
+    F6_PH(0)
+    // ---- B
+#pragma unroll
+    for (int j = 0; j < FP_QPT; ++j)
+        if (missmask & (1u << j)) S.tab[h[j]] = (uint16_t)f[j];
+    __syncthreads();   // S2
+    F6_PH(1)
+    // ---- C
+    uint32_t clean[FP_QPT], base = 0;
+    uint2* __restrict__ myrec = S.rec + warp * 128;
+#pragma unroll
+    for (int j = 0; j < FP_QPT; ++j) {
+        bool dirty = (missmask >> j) & 1u;
+        if (!dirty) dirty = S.tab[h[j]] != f[j];
+        if (GENERIC) dirty = dirty && ((validmask >> j) & 1u);
+        const uint32_t db = __ballot_sync(0xFFFFFFFFu, dirty);
+        clean[j] = GENERIC ? __ballot_sync(0xFFFFFFFFu, !dirty && ((validmask >> j) & 1u)) : ~db;
+        if (dirty) {
+            bool touched = old[j] != 0;
+            if (!touched) touched = bit_test(S.vbit, h[j]);
+            myrec[base + __popc(db & lanemask_lt())] =
+                make_uint2(h[j] | (f[j] << 16), (pos0 + 32 * j) | (touched ? F6_TOUCHED : 0u) | (old[j] << 16));
+        }
+        base += __popc(db);
+    }
+    if (lane == 0) {
+        *reinterpret_cast<uint4*>(&S.sigw[buf][warp * 4]) = make_uint4(clean[0], clean[1], clean[2], clean[3]);
+        S.cnt[warp] = base;
+    }
+    __syncwarp();
+    // deposit: one record per lane (region order == stream order, so the record index orders the members of a bucket). A record
+    // equal to the record right before it whose quad is also right before it in the stream (a run of equal quads) is a hit on that
+    // quad and changes nothing: it is dropped here (flag 1), so a run costs one mailbox entry.
+    uint2 r0 = make_uint2(0, 0);
+    bool drop0 = false;
+    {
+        uint32_t carry_x = 0xFFFFFFFFu, carry_pos = 0xFFFFFFFFu;   // record before lane 0's (previous step's lane 31)
+        #pragma unroll 1
+        for (uint32_t i0 = 0; i0 < base; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool valid = i < base;
+            uint2 r = make_uint2(0xFFFFFFFFu, 0);
+            if (valid) r = myrec[i];
+            uint32_t px = __shfl_up_sync(0xFFFFFFFFu, r.x, 1), ppos = __shfl_up_sync(0xFFFFFFFFu, r.y & 0xFFFu, 1);
+            if (lane == 0) { px = carry_x; ppos = carry_pos; }
+            const bool drop = valid && px == r.x && ppos + 1 == (r.y & 0xFFFu);
+            carry_x = __shfl_sync(0xFFFFFFFFu, r.x, 31); carry_pos = __shfl_sync(0xFFFFFFFFu, r.y & 0xFFFu, 31);
+            if (i0 == 0) { r0 = r; drop0 = drop; }
+            if (drop) {
+                const uint32_t pos = r.y & 0xFFFu;
+                atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
+                if (i0) myrec[i].y = r.y | F6_DROPPED;
+            } else if (valid) {
+                const uint32_t hh = r.x & 0xFFFFu, slot = hh & (F6_MB_SLOTS - 1), sh = (slot & 3u) * 8u;
+                const uint32_t k = (atomicAdd(&S.mbcnt[buf][slot >> 2], 1u << sh) >> sh) & 0xFFu;
+                if (k < (uint32_t)F6_MB_CAP) S.mb[slot][k] = (uint16_t)(((hh >> 12) << 12) | (warp * 128 + i));
+                else {      // fifth and later members of a slot: the shared overflow mailboxes (full hash | record index)
+                    const uint32_t s2 = slot & (F6_SEC_SLOTS - 1);
+                    const uint32_t k2 = atomicAdd(&S.seccnt[buf][s2], 1u);
+                    if (k2 < (uint32_t)F6_SEC_CAP) S.sec[s2][k2] = (hh << 12) | (warp * 128 + i);
+                    else S.overflow = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();   // S3: records, counts, clean flags and mailboxes complete; nobody reads the published values any more
+    F6_PH(2)
+    if (S.overflow) {
+        if (warp == 0) f6_replay(S, buf, run_q0, unres_run);
+    } else {
+        // ---- D
+        #pragma unroll 1
+        for (uint32_t i0 = 0; i0 < base; i0 += 32) {     // warp-uniform trip count
+            const uint32_t i = i0 + lane;
+            bool valid = i < base;
+            uint2 r = r0;
+            if (i0) r = valid ? myrec[i] : make_uint2(0, 0);
+            if (i0 ? (r.y & F6_DROPPED) != 0 : drop0) valid = false;
+            const uint32_t hh = r.x & 0xFFFFu, ff = r.x >> 16, pos = r.y & 0xFFFu, slot = hh & (F6_MB_SLOTS - 1);
+            const uint32_t myidx = warp * 128 + i;
+            bool later = false, hit = false, unres = false;
+            if (valid) {
+                const uint32_t n = (S.mbcnt[buf][slot >> 2] >> ((slot & 3u) * 8u)) & 0xFFu;
+                const uint2 e2 = *reinterpret_cast<const uint2*>(&S.mb[slot][0]);
+                const uint32_t me = ((hh >> 12) << 12) | myidx;
+                int best = -1;
+#pragma unroll
+                for (int t = 0; t < F6_MB_CAP; ++t) {
+                    const uint32_t e = ((t & 2) ? e2.y : e2.x) >> ((t & 1) * 16) & 0xFFFFu;
+                    if ((uint32_t)t < n && ((e ^ me) >> 12) == 0) {        // same bucket
+                        if (e < me) best = max(best, (int)(e & 0xFFFu));
+                        later |= e > me;
+                    }
+                }
+                if (n > (uint32_t)F6_MB_CAP) {
+                    const uint32_t s2 = slot & (F6_SEC_SLOTS - 1);
+                    const uint32_t n2 = min(S.seccnt[buf][s2], (uint32_t)F6_SEC_CAP);
+                    #pragma unroll 1
+                    for (uint32_t t = 0; t < n2; ++t) {
+                        const uint32_t e = S.sec[s2][t];
+                        if ((e >> 12) == hh) {
+                            const uint32_t ei = e & 0xFFFu;
+                            if (ei < myidx) best = max(best, (int)ei);
+                            later |= ei > myidx;
+                        }
+                    }
+                }
+                if (best >= 0) hit = (S.rec[best].x >> 16) == ff;
+                else if (r.y & F6_TOUCHED) hit = (r.y >> 16) == ff;
+                else unres = true;
+                if (!later) {
+                    S.tab[hh] = (uint16_t)ff;
+                    if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                }
+                if (hit) atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
+            }
+            f6_append_unres(unres, run_q0 + pos, r.x, &S.unres_count, unres_run);
+        }
+    }
+    __syncthreads();   // S4: dictionary and flags of the tile final
+    F6_PH(3)
+}
+
+__global__ void __launch_bounds__(F6_THREADS, 1)
+cham_flag_pass6(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_total, uint32_t nruns,
+                uint32_t* __restrict__ sigw_g, uint2* __restrict__ unres, uint32_t* __restrict__ unres_count,
+                uint32_t* __restrict__ final_tab, const uint8_t* __restrict__ copymap, const Status* __restrict__ gate)
+{
+    if (gate && !(gate->nonquiet && !gate->converged)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Flag6Smem& S = *reinterpret_cast<Flag6Smem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t run = blockIdx.x;
+    const uint64_t t_begin = (uint64_t)run * tiles_total / nruns;
+    const uint64_t t_end = (uint64_t)(run + 1) * tiles_total / nruns;
+    uint2* __restrict__ unres_run = unres + (size_t)run * 65536;
+    const uint32_t pos0 = warp * 128 + lane;
+    const uint32_t ntile_run = (uint32_t)(t_end - t_begin);
+    const uint64_t q_begin = t_begin * TILE_Q;
+    const uint64_t q_end64 = (t_end * TILE_Q < nquads) ? t_end * TILE_Q : nquads;
+    const uint32_t run_quads = q_begin < q_end64 ? (uint32_t)(q_end64 - q_begin) : 0u;
+    const uint32_t* __restrict__ rin = in + q_begin;
+    uint32_t* __restrict__ rsig = sigw_g + t_begin * (TILE_Q / 32);
+    const uint8_t* __restrict__ rcm = copymap ? copymap + t_begin * 64 : nullptr;
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* t4 = reinterpret_cast<uint4*>(S.tab);
+        #pragma unroll 1
+        for (uint32_t i = tid; i < 65536 * 2 / 16; i += F6_THREADS) t4[i] = z;
+        S.vbit[tid] = 0; S.vbit[tid + F6_THREADS] = 0;
+        S.mbcnt[0][tid] = 0; S.mbcnt[1][tid] = 0;
+        if (tid < F6_SEC_SLOTS) { S.seccnt[0][tid] = 0; S.seccnt[1][tid] = 0; }
+        if (tid == 0) { S.unres_count = 0; S.overflow = 0; }
+    }
+    __syncthreads();
+    uint32_t nxt[FP_QPT];   // register double buffer of the tile's quads
+#pragma unroll
+    for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < run_quads) ? ld_stream_u32(rin + pos0 + 32 * j) : 0u;
+    #pragma unroll 1
+    for (uint32_t lt = 0; lt < ntile_run; ++lt) {
+        uint32_t q[FP_QPT];
+        const uint32_t run_q0 = lt * TILE_Q;
+        const uint32_t left = run_q0 < run_quads ? run_quads - run_q0 : 0u;
+        const uint32_t buf = lt & 1u;
+#pragma unroll
+        for (int j = 0; j < FP_QPT; ++j) q[j] = nxt[j];
+        {
+            const uint32_t nleft = left > (uint32_t)TILE_Q ? left - TILE_Q : 0u;
+            const uint32_t* __restrict__ np = rin + run_q0 + TILE_Q + pos0;
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nleft) ? ld_stream_u32(np + 32 * j) : 0u;
+        }
+        if (left >= (uint32_t)TILE_Q && !rcm) {
+            f6_tile<false>(S, q, 0xFu, buf, run_q0, unres_run);
+        } else {
+            uint32_t validmask = 0, cp = 0;
+            if (rcm) cp = (rcm[lt * 64 + warp * 2] ? 1u : 0u) | (rcm[lt * 64 + warp * 2 + 1] ? 2u : 0u);
+#pragma unroll
+            for (int j = 0; j < FP_QPT; ++j)
+                if (pos0 + 32 * j < left && !((cp >> (j >> 1)) & 1u)) validmask |= 1u << j;
+            f6_tile<true>(S, q, validmask, buf, run_q0, unres_run);
+        }
+        if (tid < TILE_Q / 32) rsig[lt * (TILE_Q / 32) + tid] = S.sigw[buf][tid];
+        if (tid == 0) S.overflow = 0;      // read by everybody before the tile's final barrier; next written after two more barriers
+    }
+    #pragma unroll 1
+    for (uint32_t i = tid; i < 65536; i += F6_THREADS) {
+        const uint32_t v = S.tab[i];
+        const uint32_t tch = (v != 0 || bit_test(S.vbit, i)) ? 0x10000u : 0u;
+        final_tab[(size_t)run * 65536 + i] = v | tch;
+    }
+    if (tid == 0) unres_count[run] = S.unres_count < 65536u ? S.unres_count : 65536u;
+#ifdef DNS_PHASE_TIMING
+    if (tid == 0 && run == 77 && ntile_run) { const long long nt = ntile_run;
+        printf("f6 run %u tiles %lld cycles/tile: A %lld B %lld C+deposit %lld D+S4 %lld\n", run, nt, g_f6_ph[0] / nt, g_f6_ph[1] / nt,
+               g_f6_ph[2] / nt, g_f6_ph[3] / nt);
+        for (int k = 0; k < 8; ++k) g_f6_ph[k] = 0; }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------
 // carry-in tables: carry[r] = state of the dictionary before run r (as touched<<16 | fp)
 // `init` = state before run 0 (NULL: the stream start, where only bucket 0 "holds quad 0").
 // ------------------------------------------------------------------------------------------------------
@@ -1043,10 +1386,21 @@ static cudaError_t set_smem_attrs_once() {
     if (!done) {
         err = cudaFuncSetAttribute(cham_flag_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlagSmem));
         if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(cham_flag_pass6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Flag6Smem));
+        if (err == cudaSuccess)
             err = cudaFuncSetAttribute(cham_protected_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProtSmem));
         done = true;
     }
     return err;
+}
+
+int g_cham_flag_impl = 6;   // 1: barrier-phased class protocol (round 1), 6: write / verify / replay
+static void launch_flag_pass(uint32_t nruns, cudaStream_t stream, const uint32_t* in, uint64_t nquads, uint32_t ntiles, uint32_t* sigw,
+                             uint2* unres, uint32_t* unres_count, uint32_t* final_tab, const uint8_t* copymap, const Status* gate) {
+    if (g_cham_flag_impl == 1)
+        cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(in, nquads, ntiles, nruns, sigw, unres, unres_count, final_tab, copymap, gate);
+    else
+        cham_flag_pass6<<<nruns, F6_THREADS, sizeof(Flag6Smem), stream>>>(in, nquads, ntiles, nruns, sigw, unres, unres_count, final_tab, copymap, gate);
 }
 
 uint32_t cham_pick_runs(size_t nbytes, int num_sms) {
@@ -1077,8 +1431,7 @@ cudaError_t cham_encode_phase1(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
     }
     if (nblocks == 0) return cudaSuccess;
     if (ev) cudaEventRecord(ev[0], stream);
-    cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(
-        reinterpret_cast<const uint32_t*>(d_in), nquads, ntiles, nruns, reinterpret_cast<uint32_t*>(ws + L.sigw),
+    launch_flag_pass(nruns, stream, reinterpret_cast<const uint32_t*>(d_in), nquads, ntiles, reinterpret_cast<uint32_t*>(ws + L.sigw),
         reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
         reinterpret_cast<uint32_t*>(ws + L.final_tab), nullptr, nullptr);
     ++*launches;
@@ -1140,7 +1493,7 @@ cudaError_t cham_phase2_rounds(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
     }
     for (int it = it_first; it <= it_last; ++it) {
         if (it > 0) {   // flags under the current copy map (copy-mode blocks hidden from the dictionary)
-            cham_flag_pass<<<nruns, FP_THREADS, sizeof(FlagSmem), stream>>>(in32, nquads, ntiles, nruns, sigw,
+            launch_flag_pass(nruns, stream, in32, nquads, ntiles, sigw,
                 reinterpret_cast<uint2*>(ws + L.unres), reinterpret_cast<uint32_t*>(ws + L.unres_count),
                 reinterpret_cast<uint32_t*>(ws + L.final_tab), copymap, st);
             cham_carry_scan<<<65536 / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + L.final_tab), d_carry_in, 0, nruns,

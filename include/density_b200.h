@@ -191,6 +191,8 @@ DENSITY_B200_API void density_b200_shutdown(void);
 /* Test hook: cut every stage of the Cheetah / Lion copy-map iteration to k rounds (1..7, default 7) so that the host-resumed
    iteration of path 4 can be exercised on ordinary inputs. */
 DENSITY_B200_API void density_b200_test_set_stage_rounds(int k);
+/* Test / timing hook: which Chameleon flag pass kernel runs (1 = round-1 class protocol, 6 = write / verify / replay; default 6). */
+DENSITY_B200_API void density_b200_test_set_flag_impl(int k);
 /* Library version string. */
 DENSITY_B200_API const char* density_b200_version(void);
 

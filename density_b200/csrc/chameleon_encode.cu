@@ -396,23 +396,26 @@ cham_flag_pass(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles_
 // Pass 1, second formulation: write -> verify -> resolve the dirty members through a per-tile mailbox.
 //
 // Same contract as cham_flag_pass (inputs, outputs, unresolved list, last-writer table). Per 4096-quad tile:
-//   A  every quad reads the pre-tile dictionary: old != f => misser. A quad equal to the quad right before it in the stream is a hit
-//      whatever the dictionary holds (its predecessor in the bucket is that quad) and changes nothing: it is left out of everything
-//      below, so a run of equal quads costs one dictionary access.                                                       (barrier)
+//   A  every quad reads the pre-tile dictionary: old != f => misser.                                                    (barrier)
 //   B  missers store their fingerprint (racy on purpose).                                                              (barrier)
 //   C  hit members read again: unchanged => no misser in my bucket => flag 1, final. Everything else -- the missers and the hit
 //      members of a bucket some misser wrote to -- is a *dirty member* (~10 % of the quads on text). Each warp compacts its dirty
 //      members in stream order into its record region (ballot + popc) and then, one record per lane, drops the record's index into the
-//      mailbox of its bucket: 4096 slots (low 12 hash bits) x 4 entries of 16 bits (high 4 hash bits | record index).      (barrier)
+//      mailbox of its bucket: 4096 slots (low 12 hash bits) x 4 entries of 16 bits (high 4 hash bits | record index); fifth and later
+//      members of a slot go to 64 shared overflow mailboxes of 16 entries. A record equal to the record before it whose quad is also
+//      right before it in the stream (a run of equal quads) is a hit on that quad and changes nothing: it is dropped here, so a run
+//      of equal quads costs one mailbox entry.                                                                          (barrier)
 //   D  one record per lane again: the slot's entries with my bucket give my predecessor (largest smaller index: region order is
 //      stream order) => flag = predecessor's fingerprint == mine, or the pre-tile value when there is none; the member without a
 //      successor stores the bucket's final fingerprint. First touches of a bucket inside the run go to the unresolved list.  (barrier)
 // Clean buckets are never written and every dirty bucket is written once in D, so the dictionary after D is the sequential one.
-// Phases A-D do the same work in every warp whatever the data; a slot that would need a fifth entry (five dirty members of one
-// bucket, or of buckets sharing 12 hash bits, inside one tile) sends the tile to f6_replay: the in-order replay of the dirty
-// members by one warp (exact for any input, slow).
+// Phases A-D do the same work in every warp whatever the data; an overflow mailbox that would need a 17th entry (~20 dirty
+// members of one bucket inside one tile that are not one run) sends the tile to f6_replay: the in-order replay of the dirty members
+// by one warp (exact for any input, slow; 1 % of the tiles of the bench text).
 // ------------------------------------------------------------------------------------------------------
-constexpr int F6_THREADS = 1024;
+constexpr int F6_THREADS = 512, F6_QPT = 8;           // 16 warps, 8 quads per thread: one tile = TILE_Q quads
+constexpr int F6_NW = F6_THREADS / 32, F6_WQ = 32 * F6_QPT;   // warps; quads (= record region size) per warp
+static_assert(F6_THREADS * F6_QPT == TILE_Q, "tile geometry");
 constexpr int F6_MB_SLOTS = 4096, F6_MB_CAP = 4;      // mailboxes: slot = low 12 hash bits
 constexpr int F6_SEC_SLOTS = 64, F6_SEC_CAP = 16;      // overflow mailboxes shared by the slots with the same low 6 bits
 #ifdef DNS_PHASE_TIMING
@@ -433,10 +436,10 @@ struct Flag6Smem {
         uint2 dense[TILE_Q];      // fallback only (the mailboxes are void then): the same records, dense
     };
     uint32_t mbcnt[2][F6_MB_SLOTS / 4];   // entry counts, 8 bits per slot; double buffered (the idle half is cleared during the tile)
-    uint32_t sec[F6_SEC_SLOTS][F6_SEC_CAP];
+    __align__(16) uint32_t sec[F6_SEC_SLOTS][F6_SEC_CAP];
     uint32_t seccnt[2][F6_SEC_SLOTS];
     uint32_t sigw[2][TILE_Q / 32];
-    uint32_t cnt[32];
+    uint32_t cnt[32];             // records per warp (F6_NW used)
     uint32_t unres_count;
     uint32_t overflow;
 };
@@ -460,7 +463,7 @@ __device__ __forceinline__ void f6_append_unres(bool pred, uint32_t qidx_in_run,
 // (match_any for records of the same bucket inside a step).
 __device__ __noinline__ void f6_replay(Flag6Smem& S, uint32_t buf, uint32_t run_q0, uint2* __restrict__ unres_run) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t c = S.cnt[lane];
+    const uint32_t c = lane < (uint32_t)F6_NW ? S.cnt[lane] : 0u;
     uint32_t incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
@@ -474,7 +477,7 @@ __device__ __noinline__ void f6_replay(Flag6Smem& S, uint32_t buf, uint32_t run_
         for (int b = 16; b >= 1; b >>= 1) { const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (w + b - 1) & 31); if (t <= i) w += b; }
         const uint32_t e = __shfl_sync(0xFFFFFFFFu, excl, w & 31);
         if (i < n) {
-            const uint2 r = S.rec[w * 128 + (i - e)];
+            const uint2 r = S.rec[w * F6_WQ + (i - e)];
             S.dense[i] = r;
             S.tab[r.x & 0xFFFFu] = (uint16_t)(r.y >> 16);
         }
@@ -510,58 +513,63 @@ __device__ __noinline__ void f6_replay(Flag6Smem& S, uint32_t buf, uint32_t run_
 
 // One tile. GENERIC: the tile is partial or has copy-mode blocks (`validmask` bit j: my sub-row j quad takes part).
 template <bool GENERIC>
-__device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[FP_QPT], uint32_t validmask, uint32_t buf, uint32_t run_q0,
+__device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[F6_QPT], uint32_t validmask, uint32_t buf, uint32_t run_q0,
                                         uint2* __restrict__ unres_run) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t pos0 = warp * 128 + lane;
-    uint32_t h[FP_QPT], f[FP_QPT], old[FP_QPT];
+    const uint32_t pos0 = warp * F6_WQ + lane;
+    uint32_t h[F6_QPT], f[F6_QPT], old[F6_QPT];
     uint32_t missmask = 0;
     F6_PH_DECL
-    S.mbcnt[buf ^ 1u][tid] = 0;      // the other half of the mailbox counters: last read before the previous tile's final barrier
+    // the other half of the mailbox counters: last read before the previous tile's final barrier
+#pragma unroll
+    for (int k = 0; k < F6_MB_SLOTS / 4 / F6_THREADS; ++k) S.mbcnt[buf ^ 1u][tid + k * F6_THREADS] = 0;
     if (tid < F6_SEC_SLOTS) S.seccnt[buf ^ 1u][tid] = 0;
     // ---- A
 #pragma unroll
-    for (int j = 0; j < FP_QPT; ++j) {
+    for (int j = 0; j < F6_QPT; ++j) {
         const uint32_t p = hash_prod(q[j]);
         h[j] = prod_hash(p);
         f[j] = prod_fp(p, q[j]);
         old[j] = S.tab[h[j]];
     }
+    uint32_t fmin = f[0];
 #pragma unroll
-    for (int j = 0; j < FP_QPT; ++j) {
+    for (int j = 0; j < F6_QPT; ++j) {
         bool miss = old[j] != f[j];
-        if (f[j] == 0 && old[j] == 0) miss = !bit_test(S.vbit, h[j]);   // fingerprint 0 is also what an untouched bucket shows
         if (GENERIC) miss = miss && ((validmask >> j) & 1u);
         if (miss) missmask |= 1u << j;
+        fmin = min(fmin, f[j]);
+    }
+    if (fmin == 0) {   // fingerprint 0 is also what an untouched bucket shows: "equal" is a hit only if the bucket was touched (rare path)
+#pragma unroll
+        for (int j = 0; j < F6_QPT; ++j)
+            if (f[j] == 0 && old[j] == 0 && (!GENERIC || ((validmask >> j) & 1u)) && !bit_test(S.vbit, h[j])) missmask |= 1u << j;
     }
     __syncthreads();   // S1: every read of the pre-tile dictionary precedes the publishes
     F6_PH(0)
     // ---- B
 #pragma unroll
-    for (int j = 0; j < FP_QPT; ++j)
+    for (int j = 0; j < F6_QPT; ++j)
         if (missmask & (1u << j)) S.tab[h[j]] = (uint16_t)f[j];
     __syncthreads();   // S2
     F6_PH(1)
     // ---- C
-    uint32_t clean[FP_QPT], base = 0;
-    uint2* __restrict__ myrec = S.rec + warp * 128;
+    uint32_t clean[F6_QPT], base = 0;
+    uint2* __restrict__ myrec = S.rec + warp * F6_WQ;
 #pragma unroll
-    for (int j = 0; j < FP_QPT; ++j) {
+    for (int j = 0; j < F6_QPT; ++j) {
         bool dirty = (missmask >> j) & 1u;
         if (!dirty) dirty = S.tab[h[j]] != f[j];
         if (GENERIC) dirty = dirty && ((validmask >> j) & 1u);
         const uint32_t db = __ballot_sync(0xFFFFFFFFu, dirty);
         clean[j] = GENERIC ? __ballot_sync(0xFFFFFFFFu, !dirty && ((validmask >> j) & 1u)) : ~db;
-        if (dirty) {
-            bool touched = old[j] != 0;
-            if (!touched) touched = bit_test(S.vbit, h[j]);
-            myrec[base + __popc(db & lanemask_lt())] =
-                make_uint2(h[j] | (f[j] << 16), (pos0 + 32 * j) | (touched ? F6_TOUCHED : 0u) | (old[j] << 16));
-        }
+        if (dirty) myrec[base + __popc(db & lanemask_lt())] = make_uint2(h[j] | (f[j] << 16), (pos0 + 32 * j) | (old[j] << 16));
         base += __popc(db);
     }
     if (lane == 0) {
-        *reinterpret_cast<uint4*>(&S.sigw[buf][warp * 4]) = make_uint4(clean[0], clean[1], clean[2], clean[3]);
+#pragma unroll
+        for (int j = 0; j < F6_QPT; j += 4)
+            *reinterpret_cast<uint4*>(&S.sigw[buf][warp * F6_QPT + j]) = make_uint4(clean[j], clean[j + 1], clean[j + 2], clean[j + 3]);
         S.cnt[warp] = base;
     }
     __syncwarp();
@@ -577,7 +585,11 @@ __device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[FP_QPT
             const uint32_t i = i0 + lane;
             const bool valid = i < base;
             uint2 r = make_uint2(0xFFFFFFFFu, 0);
-            if (valid) r = myrec[i];
+            if (valid) {
+                r = myrec[i];
+                // "bucket touched before this tile": the pre-tile fingerprint, or the touched bit when that is 0 (stable until phase D)
+                if ((r.y >> 16) != 0 || bit_test(S.vbit, r.x & 0xFFFFu)) r.y |= F6_TOUCHED;
+            }
             uint32_t px = __shfl_up_sync(0xFFFFFFFFu, r.x, 1), ppos = __shfl_up_sync(0xFFFFFFFFu, r.y & 0xFFFu, 1);
             if (lane == 0) { px = carry_x; ppos = carry_pos; }
             const bool drop = valid && px == r.x && ppos + 1 == (r.y & 0xFFFu);
@@ -588,13 +600,14 @@ __device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[FP_QPT
                 atomicOr(&S.sigw[buf][pos >> 5], 1u << (pos & 31));
                 if (i0) myrec[i].y = r.y | F6_DROPPED;
             } else if (valid) {
+                if (i0 && (r.y & F6_TOUCHED)) myrec[i].y = r.y;
                 const uint32_t hh = r.x & 0xFFFFu, slot = hh & (F6_MB_SLOTS - 1), sh = (slot & 3u) * 8u;
                 const uint32_t k = (atomicAdd(&S.mbcnt[buf][slot >> 2], 1u << sh) >> sh) & 0xFFu;
-                if (k < (uint32_t)F6_MB_CAP) S.mb[slot][k] = (uint16_t)(((hh >> 12) << 12) | (warp * 128 + i));
+                if (k < (uint32_t)F6_MB_CAP) S.mb[slot][k] = (uint16_t)(((hh >> 12) << 12) | (warp * F6_WQ + i));
                 else {      // fifth and later members of a slot: the shared overflow mailboxes (full hash | record index)
                     const uint32_t s2 = slot & (F6_SEC_SLOTS - 1);
                     const uint32_t k2 = atomicAdd(&S.seccnt[buf][s2], 1u);
-                    if (k2 < (uint32_t)F6_SEC_CAP) S.sec[s2][k2] = (hh << 12) | (warp * 128 + i);
+                    if (k2 < (uint32_t)F6_SEC_CAP) S.sec[s2][k2] = (hh << 12) | (warp * F6_WQ + i);
                     else S.overflow = 1;
                 }
             }
@@ -602,6 +615,9 @@ __device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[FP_QPT
     }
     __syncthreads();   // S3: records, counts, clean flags and mailboxes complete; nobody reads the published values any more
     F6_PH(2)
+#ifdef DNS_PHASE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 77) { g_f6_ph[6] += S.overflow; uint32_t tot = 0; for (int w = 0; w < 32; ++w) tot += S.cnt[w]; g_f6_ph[7] += tot; }
+#endif
     if (S.overflow) {
         if (warp == 0) f6_replay(S, buf, run_q0, unres_run);
     } else {
@@ -614,7 +630,7 @@ __device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[FP_QPT
             if (i0) r = valid ? myrec[i] : make_uint2(0, 0);
             if (i0 ? (r.y & F6_DROPPED) != 0 : drop0) valid = false;
             const uint32_t hh = r.x & 0xFFFFu, ff = r.x >> 16, pos = r.y & 0xFFFu, slot = hh & (F6_MB_SLOTS - 1);
-            const uint32_t myidx = warp * 128 + i;
+            const uint32_t myidx = warp * F6_WQ + i;
             bool later = false, hit = false, unres = false;
             if (valid) {
                 const uint32_t n = (S.mbcnt[buf][slot >> 2] >> ((slot & 3u) * 8u)) & 0xFFu;
@@ -631,14 +647,19 @@ __device__ __forceinline__ void f6_tile(Flag6Smem& S, const uint32_t (&q)[FP_QPT
                 }
                 if (n > (uint32_t)F6_MB_CAP) {
                     const uint32_t s2 = slot & (F6_SEC_SLOTS - 1);
-                    const uint32_t n2 = min(S.seccnt[buf][s2], (uint32_t)F6_SEC_CAP);
+                    const uint32_t n2 = S.seccnt[buf][s2];     // <= F6_SEC_CAP here (else the tile overflowed)
+                    const uint32_t mine = (hh << 12) | myidx;
                     #pragma unroll 1
-                    for (uint32_t t = 0; t < n2; ++t) {
-                        const uint32_t e = S.sec[s2][t];
-                        if ((e >> 12) == hh) {
-                            const uint32_t ei = e & 0xFFFu;
-                            if (ei < myidx) best = max(best, (int)ei);
-                            later |= ei > myidx;
+                    for (uint32_t t4 = 0; t4 < n2; t4 += 4) {
+                        const uint4 e4 = *reinterpret_cast<const uint4*>(&S.sec[s2][t4]);
+                        const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const uint32_t e = ev[t];
+                            if (t4 + t < n2 && ((e ^ mine) & 0xFFFFF000u) == 0) {
+                                if (e < mine) best = max(best, (int)(e & 0xFFFu));
+                                later |= e > mine;
+                            }
                         }
                     }
                 }
@@ -671,7 +692,7 @@ cham_flag_pass6(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles
     const uint64_t t_begin = (uint64_t)run * tiles_total / nruns;
     const uint64_t t_end = (uint64_t)(run + 1) * tiles_total / nruns;
     uint2* __restrict__ unres_run = unres + (size_t)run * 65536;
-    const uint32_t pos0 = warp * 128 + lane;
+    const uint32_t pos0 = warp * F6_WQ + lane;
     const uint32_t ntile_run = (uint32_t)(t_end - t_begin);
     const uint64_t q_begin = t_begin * TILE_Q;
     const uint64_t q_end64 = (t_end * TILE_Q < nquads) ? t_end * TILE_Q : nquads;
@@ -684,36 +705,46 @@ cham_flag_pass6(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles
         uint4* t4 = reinterpret_cast<uint4*>(S.tab);
         #pragma unroll 1
         for (uint32_t i = tid; i < 65536 * 2 / 16; i += F6_THREADS) t4[i] = z;
-        S.vbit[tid] = 0; S.vbit[tid + F6_THREADS] = 0;
-        S.mbcnt[0][tid] = 0; S.mbcnt[1][tid] = 0;
+        #pragma unroll 1
+        for (uint32_t i = tid; i < 2048; i += F6_THREADS) S.vbit[i] = 0;
+        #pragma unroll 1
+        for (uint32_t i = tid; i < F6_MB_SLOTS / 4; i += F6_THREADS) { S.mbcnt[0][i] = 0; S.mbcnt[1][i] = 0; }
         if (tid < F6_SEC_SLOTS) { S.seccnt[0][tid] = 0; S.seccnt[1][tid] = 0; }
         if (tid == 0) { S.unres_count = 0; S.overflow = 0; }
     }
     __syncthreads();
-    uint32_t nxt[FP_QPT];   // register double buffer of the tile's quads
+    uint32_t nxt[F6_QPT];   // register double buffer of the tile's quads
 #pragma unroll
-    for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < run_quads) ? ld_stream_u32(rin + pos0 + 32 * j) : 0u;
+    for (int j = 0; j < F6_QPT; ++j) nxt[j] = (pos0 + 32 * j < run_quads) ? ld_stream_u32(rin + pos0 + 32 * j) : 0u;
     #pragma unroll 1
     for (uint32_t lt = 0; lt < ntile_run; ++lt) {
-        uint32_t q[FP_QPT];
+        uint32_t q[F6_QPT];
         const uint32_t run_q0 = lt * TILE_Q;
         const uint32_t left = run_q0 < run_quads ? run_quads - run_q0 : 0u;
         const uint32_t buf = lt & 1u;
 #pragma unroll
-        for (int j = 0; j < FP_QPT; ++j) q[j] = nxt[j];
+        for (int j = 0; j < F6_QPT; ++j) q[j] = nxt[j];
         {
             const uint32_t nleft = left > (uint32_t)TILE_Q ? left - TILE_Q : 0u;
             const uint32_t* __restrict__ np = rin + run_q0 + TILE_Q + pos0;
+            if (nleft >= (uint32_t)TILE_Q) {
 #pragma unroll
-            for (int j = 0; j < FP_QPT; ++j) nxt[j] = (pos0 + 32 * j < nleft) ? ld_stream_u32(np + 32 * j) : 0u;
+                for (int j = 0; j < F6_QPT; ++j) nxt[j] = ld_stream_u32(np + 32 * j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < F6_QPT; ++j) nxt[j] = (pos0 + 32 * j < nleft) ? ld_stream_u32(np + 32 * j) : 0u;
+            }
         }
         if (left >= (uint32_t)TILE_Q && !rcm) {
-            f6_tile<false>(S, q, 0xFu, buf, run_q0, unres_run);
+            f6_tile<false>(S, q, (1u << F6_QPT) - 1u, buf, run_q0, unres_run);
         } else {
             uint32_t validmask = 0, cp = 0;
-            if (rcm) cp = (rcm[lt * 64 + warp * 2] ? 1u : 0u) | (rcm[lt * 64 + warp * 2 + 1] ? 2u : 0u);
+            if (rcm) {
 #pragma unroll
-            for (int j = 0; j < FP_QPT; ++j)
+                for (int b = 0; b < F6_WQ / 64; ++b) cp |= (rcm[lt * 64 + warp * (F6_WQ / 64) + b] ? 1u : 0u) << b;
+            }
+#pragma unroll
+            for (int j = 0; j < F6_QPT; ++j)
                 if (pos0 + 32 * j < left && !((cp >> (j >> 1)) & 1u)) validmask |= 1u << j;
             f6_tile<true>(S, q, validmask, buf, run_q0, unres_run);
         }
@@ -729,8 +760,8 @@ cham_flag_pass6(const uint32_t* __restrict__ in, uint64_t nquads, uint32_t tiles
     if (tid == 0) unres_count[run] = S.unres_count < 65536u ? S.unres_count : 65536u;
 #ifdef DNS_PHASE_TIMING
     if (tid == 0 && run == 77 && ntile_run) { const long long nt = ntile_run;
-        printf("f6 run %u tiles %lld cycles/tile: A %lld B %lld C+deposit %lld D+S4 %lld\n", run, nt, g_f6_ph[0] / nt, g_f6_ph[1] / nt,
-               g_f6_ph[2] / nt, g_f6_ph[3] / nt);
+        printf("f6 run %u tiles %lld cycles/tile: A %lld B %lld C+deposit %lld D+S4 %lld  overflow tiles %lld dirty/tile %lld\n", run, nt, g_f6_ph[0] / nt, g_f6_ph[1] / nt,
+               g_f6_ph[2] / nt, g_f6_ph[3] / nt, g_f6_ph[6], g_f6_ph[7] / nt);
         for (int k = 0; k < 8; ++k) g_f6_ph[k] = 0; }
 #endif
 }

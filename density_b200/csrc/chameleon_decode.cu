@@ -339,6 +339,320 @@ cham_decode_pass(const uint8_t* __restrict__ in, const uint64_t* __restrict__ bl
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Decode pass, second formulation (same contract as cham_decode_pass; the structure of the round-2 encoder flag pass,
+// chameleon_encode.cu cham_flag_pass6: nothing but loads, compares and ballots on the per-quad path; atomics and searches only on
+// the few "dirty" quads, one record per lane).  512 threads, 8 quads per thread, tile = 4096 quads = 64 blocks:
+//   A  readers (MAP quads) read the pre-tile dictionary; writers (PLAIN quads, ~7 %) compute hash and fingerprint.        (barrier)
+//   B  writers store their fingerprint (racy on purpose) and raise the bucket's byte in a hashed per-tile mark map.        (barrier)
+//   C  raw and PLAIN quads go out as they are; a reader whose mark byte is clear saw no writer of its bucket in this tile: the
+//      pre-tile value is its value (coalesced store). Writers and the remaining readers (suspects) are compacted in stream order into
+//      the warp's record region; writers drop their record index into the mailbox of their bucket (4096 slots x 4 + overflow).  (barrier)
+//   D  one record per lane: a suspect takes the fingerprint of the writer with the largest smaller index in its bucket, or its own
+//      pre-tile value; the writer without a successor leaves the bucket's final fingerprint and clears the mark.            (barrier)
+// WONLY (writer pass: the run's last-writer table only) needs A, the deposit and D.
+// A mailbox overflow (more than ~20 PLAIN quads of one bucket in one tile) sends the tile to d7_replay (one warp, in order).
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int D7_THREADS = 512, D7_QPT = 8, D7_NW = D7_THREADS / 32, D7_WQ = 32 * D7_QPT;
+static_assert(D7_THREADS * D7_QPT == TILE_Q, "tile geometry");
+constexpr int D7_MB_SLOTS = 4096, D7_MB_CAP = 4, D7_SEC_SLOTS = 64, D7_SEC_CAP = 16, D7_MARK_N = 8192;
+constexpr uint32_t D7_TOUCHED = 1u << 12, D7_WRITER = 1u << 13;   // record.y: pos (12) | touched | writer | pre-tile fingerprint << 16
+
+struct Dec7Smem {
+    uint16_t tab[65536];
+    uint32_t vbit[2048];
+    uint2 rec[TILE_Q];            // warp w: records [256 w, 256 w + cnt[w]) in stream order. x = hash | fp << 16 (fp: writers), y see above
+    union {
+        uint16_t mb[D7_MB_SLOTS][D7_MB_CAP];     // writers only: (hash >> 12) << 12 | record index
+        uint32_t wseen[2048];                    // fallback only: bucket written so far in this tile
+    };
+    uint32_t mbcnt[2][D7_MB_SLOTS / 4];
+    __align__(16) uint32_t sec[D7_SEC_SLOTS][D7_SEC_CAP];
+    uint32_t seccnt[2][D7_SEC_SLOTS];
+    uint8_t wmark[D7_MARK_N];     // per tile: some writer's bucket hashes here
+    unsigned long long boff[2][64];
+    uint32_t bsig[2][128];
+    uint32_t bcopy[2][2];
+    uint32_t cnt[32];
+    uint32_t overflow;
+};
+static_assert(sizeof(Dec7Smem) <= 227 * 1024, "decode pass shared memory");
+
+template <class SM>
+__device__ __forceinline__ void stage_tile7(SM& S, int buf, const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, uint64_t b0, uint64_t nblocks) {
+    const uint32_t tid = threadIdx.x;
+    if (tid < 64) {     // warps 0 and 1, whole warps
+        unsigned long long o = 0; uint32_t lo = 0, hi = 0; bool copied = false;
+        if (b0 + tid < nblocks) {
+            o = blk_off[b0 + tid];
+            copied = (o & BLK_COPY) != 0;
+            o &= ~BLK_COPY;
+            if (!copied) {
+                const uint8_t* p = in + o;
+                lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
+                o += 8;
+            }
+        }
+        S.boff[buf][tid] = o; S.bsig[buf][2 * tid] = lo; S.bsig[buf][2 * tid + 1] = hi;
+        const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, copied);
+        if ((tid & 31) == 0) S.bcopy[buf][tid >> 5] = cmask;
+    }
+}
+template <bool WONLY>
+__device__ __forceinline__ void fetch_payload7(const Dec7Smem& S, int buf, const uint8_t* __restrict__ in, uint32_t nb_tile, uint32_t (&v)[D7_QPT]) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < D7_QPT; ++j) {
+        const uint32_t bl = warp * (D7_WQ / 64) + (j >> 1);
+        const uint32_t k = (j & 1) * 32 + lane;
+        v[j] = 0;
+        if (bl < nb_tile) {
+            const uint32_t lo = S.bsig[buf][2 * bl], hi = S.bsig[buf][2 * bl + 1];
+            const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
+            const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
+            const uint8_t* p = in + S.boff[buf][bl] + 4 * k - 2 * before;
+            if (flag) { if (!WONLY) v[j] = ldu16(p); }
+            else v[j] = ldu16(p) | (ldu16(p + 2) << 16);
+        }
+    }
+}
+
+// Fallback: the tile's writers and suspects in stream order by one warp.
+template <bool WONLY>
+__device__ __noinline__ void d7_replay(Dec7Smem& S, uint32_t* __restrict__ out, uint64_t q0) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = lane; i < 2048; i += 32) S.wseen[i] = 0;
+    const uint32_t c = lane < (uint32_t)D7_NW ? S.cnt[lane] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+    const uint32_t excl = incl - c;
+    const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    __syncwarp();
+    #pragma unroll 1
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n;
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 16; b >= 1; b >>= 1) { const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (w + b - 1) & 31); if (t <= i) w += b; }
+        const uint32_t e = __shfl_sync(0xFFFFFFFFu, excl, w & 31);
+        uint2 r = make_uint2(0, 0);
+        if (valid) r = S.rec[w * D7_WQ + (i - e)];
+        const uint32_t hh = r.x & 0xFFFFu, ff = r.x >> 16, pos = r.y & 0xFFFu;
+        const bool writer = valid && (r.y & D7_WRITER);
+        const uint32_t grp = __match_any_sync(0xFFFFFFFFu, valid ? hh : 0x10000u + lane);
+        const uint32_t wm = __ballot_sync(0xFFFFFFFFu, writer);
+        const uint32_t lw = grp & wm & lanemask_lt();              // earlier writers of my bucket inside the step
+        const uint32_t fprev = __shfl_sync(0xFFFFFFFFu, ff, lw ? 31 - __clz(lw) : 0);
+        if (valid && !writer && !WONLY) {
+            uint32_t fv = r.y >> 16; bool have = (r.y & D7_TOUCHED) != 0;
+            if (lw) { fv = fprev; have = true; }
+            else if ((S.wseen[hh >> 5] >> (hh & 31)) & 1u) { fv = S.tab[hh]; have = true; }
+            out[q0 + pos] = have ? quad_from_hf(hh, fv) : 0u;
+        }
+        __syncwarp();
+        if (writer && (grp & wm & lanemask_gt()) == 0) {           // last writer of the bucket inside the step
+            S.tab[hh] = (uint16_t)ff;
+            if (ff == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+            atomicOr(&S.wseen[hh >> 5], 1u << (hh & 31));
+            S.wmark[hh & (D7_MARK_N - 1)] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+template <bool WONLY>
+__global__ void __launch_bounds__(D7_THREADS, 1)
+cham_decode_pass7(const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, DecStatus* st,
+                  uint32_t nruns, uint32_t* __restrict__ out /* quads */, const uint32_t* __restrict__ carry,
+                  uint32_t* __restrict__ final_tab) {
+    if (st->nonquiet || st->error) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Dec7Smem& S = *reinterpret_cast<Dec7Smem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t run = blockIdx.x;
+    const uint64_t nblocks = st->main_blocks;
+    const uint64_t ntiles = (nblocks + 63) / 64;
+    const uint64_t t_begin = (uint64_t)run * ntiles / nruns, t_end = (uint64_t)(run + 1) * ntiles / nruns;
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* t4 = reinterpret_cast<uint4*>(S.tab);
+        for (uint32_t i = tid; i < 65536 * 2 / 16; i += D7_THREADS) t4[i] = z;
+        for (uint32_t i = tid; i < 2048; i += D7_THREADS) S.vbit[i] = 0;
+        for (uint32_t i = tid; i < D7_MB_SLOTS / 4; i += D7_THREADS) { S.mbcnt[0][i] = 0; S.mbcnt[1][i] = 0; }
+        for (uint32_t i = tid; i < D7_MARK_N / 4; i += D7_THREADS) reinterpret_cast<uint32_t*>(S.wmark)[i] = 0;
+        if (tid < D7_SEC_SLOTS) { S.seccnt[0][tid] = 0; S.seccnt[1][tid] = 0; }
+        if (tid == 0) S.overflow = 0;
+        if (!WONLY) {
+            __syncthreads();
+            const uint32_t* __restrict__ cr = carry + (size_t)run * 65536;   // dictionary before this run
+            for (uint32_t i = tid; i < 65536; i += D7_THREADS) {
+                const uint32_t c = cr[i];
+                if (c & 0x10000u) {
+                    S.tab[i] = (uint16_t)c;
+                    if ((c & 0xFFFFu) == 0) atomicOr(&S.vbit[i >> 5], 1u << (i & 31));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t nval[D7_QPT];
+    if (t_begin < t_end) stage_tile7(S, 0, in, blk_off, t_begin * 64, nblocks);
+    __syncthreads();
+    if (t_begin < t_end) fetch_payload7<WONLY>(S, 0, in, (uint32_t)((nblocks - t_begin * 64 < 64) ? (nblocks - t_begin * 64) : 64), nval);
+
+    for (uint64_t t = t_begin; t < t_end; ++t) {
+        const uint64_t b0 = t * 64;
+        const uint32_t nb_tile = (uint32_t)((nblocks - b0 < 64) ? (nblocks - b0) : 64);
+        const int cur = (int)((t - t_begin) & 1);
+        const uint32_t buf = (uint32_t)cur;
+        if (t + 1 < t_end) stage_tile7(S, cur ^ 1, in, blk_off, b0 + 64, nblocks);
+#pragma unroll
+        for (int k = 0; k < D7_MB_SLOTS / 4 / D7_THREADS; ++k) S.mbcnt[buf ^ 1u][tid + k * D7_THREADS] = 0;
+        if (tid < D7_SEC_SLOTS) S.seccnt[buf ^ 1u][tid] = 0;
+
+        // ---- A
+        uint32_t val[D7_QPT], hk[D7_QPT], fa[D7_QPT];   // val: the quad (PLAIN / raw) or the hash (MAP); hk: hash; fa: readers pre-tile fp, writers own fp
+        uint32_t act = 0, wr = 0, raw = 0, tch = 0;     // bit j
+#pragma unroll
+        for (int j = 0; j < D7_QPT; ++j) {
+            const uint32_t bl = warp * (D7_WQ / 64) + (j >> 1);
+            val[j] = nval[j]; hk[j] = 0; fa[j] = 0;
+            if (bl < nb_tile) {
+                act |= 1u << j;
+                const uint32_t flag = (S.bsig[cur][2 * bl + (j & 1)] >> lane) & 1u;
+                if ((S.bcopy[cur][bl >> 5] >> (bl & 31)) & 1u) raw |= 1u << j;
+                else if (flag) {
+                    if (!WONLY) {
+                        hk[j] = val[j];
+                        fa[j] = S.tab[hk[j]];
+                        if (fa[j] != 0 || bit_test(S.vbit, hk[j])) tch |= 1u << j;
+                    }
+                } else {
+                    wr |= 1u << j;
+                    const uint32_t p = hash_prod(val[j]);
+                    hk[j] = prod_hash(p); fa[j] = prod_fp(p, val[j]);
+                }
+            }
+        }
+        __syncthreads();  // S1: readers have read the pre-tile dictionary; next tile's signatures staged
+        if (t + 1 < t_end)   // payload of the next tile: in flight during the rest of this tile
+            fetch_payload7<WONLY>(S, cur ^ 1, in, (uint32_t)((nblocks - (b0 + 64) < 64) ? (nblocks - (b0 + 64)) : 64), nval);
+        if (!WONLY) {
+            // ---- B
+#pragma unroll
+            for (int j = 0; j < D7_QPT; ++j)
+                if ((wr >> j) & 1u) { S.tab[hk[j]] = (uint16_t)fa[j]; S.wmark[hk[j] & (D7_MARK_N - 1)] = 1; }
+            __syncthreads();  // S2
+        }
+        // ---- C
+        const uint64_t q0 = b0 * 64;   // first output quad of the tile
+        uint32_t base = 0;
+        uint2* __restrict__ myrec = S.rec + warp * D7_WQ;
+#pragma unroll
+        for (int j = 0; j < D7_QPT; ++j) {
+            const uint32_t pos = warp * D7_WQ + j * 32 + lane;
+            const bool active = (act >> j) & 1u, writer = (wr >> j) & 1u;
+            bool dirty = writer;
+            if (!WONLY && active) {
+                if (writer || ((raw >> j) & 1u)) out[q0 + pos] = val[j];
+                else if (S.wmark[hk[j] & (D7_MARK_N - 1)] == 0)
+                    out[q0 + pos] = ((tch >> j) & 1u) ? quad_from_hf(hk[j], fa[j]) : 0u;      // empty bucket -> 0 (chameleon.rs:41)
+                else dirty = true;
+            }
+            const uint32_t db = __ballot_sync(0xFFFFFFFFu, dirty);
+            if (dirty) myrec[base + __popc(db & lanemask_lt())] =
+                make_uint2(hk[j] | (writer ? fa[j] << 16 : 0u), pos | (((tch >> j) & 1u) ? D7_TOUCHED : 0u) | (writer ? D7_WRITER : 0u) | (writer ? 0u : fa[j] << 16));
+            base += __popc(db);
+        }
+        if (lane == 0) S.cnt[warp] = base;
+        __syncwarp();
+        // deposit (writers only)
+        uint2 r0 = make_uint2(0, 0);
+        #pragma unroll 1
+        for (uint32_t i = lane; i < base; i += 32) {
+            const uint2 r = myrec[i];
+            if (i < 32) r0 = r;
+            if (r.y & D7_WRITER) {
+                const uint32_t hh = r.x & 0xFFFFu, slot = hh & (D7_MB_SLOTS - 1), sh = (slot & 3u) * 8u;
+                const uint32_t k = (atomicAdd(&S.mbcnt[buf][slot >> 2], 1u << sh) >> sh) & 0xFFu;
+                if (k < (uint32_t)D7_MB_CAP) S.mb[slot][k] = (uint16_t)(((hh >> 12) << 12) | (warp * D7_WQ + i));
+                else {
+                    const uint32_t s2 = slot & (D7_SEC_SLOTS - 1);
+                    const uint32_t k2 = atomicAdd(&S.seccnt[buf][s2], 1u);
+                    if (k2 < (uint32_t)D7_SEC_CAP) S.sec[s2][k2] = (hh << 12) | (warp * D7_WQ + i);
+                    else S.overflow = 1;
+                }
+            }
+        }
+        __syncthreads();  // S3
+        if (S.overflow) {
+            if (warp == 0) d7_replay<WONLY>(S, out, q0);
+        } else {
+            // ---- D
+            #pragma unroll 1
+            for (uint32_t i0 = 0; i0 < base; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool valid = i < base;
+                uint2 r = r0;
+                if (i0) r = valid ? myrec[i] : make_uint2(0, 0);
+                if (valid) {
+                    const uint32_t hh = r.x & 0xFFFFu, slot = hh & (D7_MB_SLOTS - 1), myidx = warp * D7_WQ + i;
+                    const uint32_t n = (S.mbcnt[buf][slot >> 2] >> ((slot & 3u) * 8u)) & 0xFFu;
+                    const uint2 e2 = *reinterpret_cast<const uint2*>(&S.mb[slot][0]);
+                    const uint32_t me = ((hh >> 12) << 12) | myidx;
+                    int best = -1; bool later = false;
+#pragma unroll
+                    for (int tt = 0; tt < D7_MB_CAP; ++tt) {
+                        const uint32_t e = ((tt & 2) ? e2.y : e2.x) >> ((tt & 1) * 16) & 0xFFFFu;
+                        if ((uint32_t)tt < n && ((e ^ me) >> 12) == 0) {
+                            if (e < me) best = max(best, (int)(e & 0xFFFu));
+                            later |= e > me;
+                        }
+                    }
+                    if (n > (uint32_t)D7_MB_CAP) {
+                        const uint32_t s2 = slot & (D7_SEC_SLOTS - 1);
+                        const uint32_t n2 = S.seccnt[buf][s2];
+                        const uint32_t mine = (hh << 12) | myidx;
+                        #pragma unroll 1
+                        for (uint32_t t4 = 0; t4 < n2; t4 += 4) {
+                            const uint4 e4 = *reinterpret_cast<const uint4*>(&S.sec[s2][t4]);
+                            const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                            for (int tt = 0; tt < 4; ++tt) {
+                                const uint32_t e = ev[tt];
+                                if (t4 + tt < n2 && ((e ^ mine) & 0xFFFFF000u) == 0) {
+                                    if (e < mine) best = max(best, (int)(e & 0xFFFu));
+                                    later |= e > mine;
+                                }
+                            }
+                        }
+                    }
+                    if (r.y & D7_WRITER) {
+                        if (!later) {      // chameleon.rs:59: the last PLAIN quad of the bucket leaves its value
+                            S.tab[hh] = (uint16_t)(r.x >> 16);
+                            if ((r.x >> 16) == 0) atomicOr(&S.vbit[hh >> 5], 1u << (hh & 31));
+                            S.wmark[hh & (D7_MARK_N - 1)] = 0;
+                        }
+                    } else if (!WONLY) {
+                        uint32_t fv = r.y >> 16; bool have = (r.y & D7_TOUCHED) != 0;
+                        if (best >= 0) { fv = S.rec[best].x >> 16; have = true; }
+                        out[q0 + (r.y & 0xFFFu)] = have ? quad_from_hf(hh, fv) : 0u;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // S4
+        if (tid == 0) S.overflow = 0;
+    }
+    for (uint32_t i = tid; i < 65536; i += D7_THREADS) {
+        const uint32_t v = S.tab[i];
+        const uint32_t tchd = (v != 0 || bit_test(S.vbit, i)) ? 0x10000u : 0u;
+        final_tab[(size_t)run * 65536 + i] = v | tchd;
+    }
+}
+
 // carry-in fold for decode: initial dictionary is all zero values (chameleon.rs:41): nothing touched.
 __global__ void dec_carry_scan(const uint32_t* __restrict__ final_tab, uint32_t nruns, uint32_t* __restrict__ carry, uint32_t* __restrict__ dict_out) {
     uint32_t hb = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,6 +739,8 @@ __global__ void dec_tail(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __
 
 using namespace chamdec;
 
+int g_cham_decode_impl = 7;   // 1: round-1 decode pass, 7: write / verify / mailbox (timing comparisons and tests)
+
 struct ChamDecLayout { bounds::BoundsLayout B; size_t final_tab, carry, dict, total; };
 
 static size_t dec_layout(size_t nbytes, size_t cap, int nruns_max, ChamDecLayout* L) {
@@ -447,6 +763,8 @@ cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     if (!attr_done) {
         cudaError_t e0 = cudaFuncSetAttribute(cham_decode_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
         if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(cham_decode_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+        if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(cham_decode_pass7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dec7Smem));
+        if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(cham_decode_pass7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dec7Smem));
         if (e0 != cudaSuccess) return e0;
         attr_done = true;
     }
@@ -461,9 +779,13 @@ cudaError_t cham_decode_parallel(const uint8_t* d_in, size_t nbytes, uint8_t* d_
     uint32_t nruns = (uint32_t)(tiles_ub / 16); if (nruns < 1) nruns = 1; if (nruns > (uint32_t)num_sms) nruns = num_sms;
     uint32_t* final_tab = reinterpret_cast<uint32_t*>(ws + L.final_tab);
     uint32_t* carry = reinterpret_cast<uint32_t*>(ws + L.carry);
-    cham_decode_pass<true><<<nruns, DP_THREADS, sizeof(DecSmem), stream>>>(d_in, blk_off, st, nruns, nullptr, nullptr, final_tab); ++*launches;
+    if (g_cham_decode_impl == 1) cham_decode_pass<true><<<nruns, DP_THREADS, sizeof(DecSmem), stream>>>(d_in, blk_off, st, nruns, nullptr, nullptr, final_tab);
+    else cham_decode_pass7<true><<<nruns, D7_THREADS, sizeof(Dec7Smem), stream>>>(d_in, blk_off, st, nruns, nullptr, nullptr, final_tab);
+    ++*launches;
     dec_carry_scan<<<65536 / 256, 256, 0, stream>>>(final_tab, nruns, carry, reinterpret_cast<uint32_t*>(ws + L.dict)); ++*launches;
-    cham_decode_pass<false><<<nruns, DP_THREADS, sizeof(DecSmem), stream>>>(d_in, blk_off, st, nruns, reinterpret_cast<uint32_t*>(d_out), carry, final_tab); ++*launches;
+    if (g_cham_decode_impl == 1) cham_decode_pass<false><<<nruns, DP_THREADS, sizeof(DecSmem), stream>>>(d_in, blk_off, st, nruns, reinterpret_cast<uint32_t*>(d_out), carry, final_tab);
+    else cham_decode_pass7<false><<<nruns, D7_THREADS, sizeof(Dec7Smem), stream>>>(d_in, blk_off, st, nruns, reinterpret_cast<uint32_t*>(d_out), carry, final_tab);
+    ++*launches;
     dec_tail<<<1, 32, 0, stream>>>(d_in, nbytes, d_out, cap, reinterpret_cast<uint32_t*>(ws + L.dict), st, d_out_size); ++*launches;
     e = cudaMemcpyAsync(d_nonquiet, &st->nonquiet, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return e;

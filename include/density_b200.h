@@ -193,6 +193,8 @@ DENSITY_B200_API void density_b200_shutdown(void);
 DENSITY_B200_API void density_b200_test_set_stage_rounds(int k);
 /* Test / timing hook: which Chameleon flag pass kernel runs (1 = round-1 class protocol, 6 = write / verify / replay; default 6). */
 DENSITY_B200_API void density_b200_test_set_flag_impl(int k);
+/* Same for the Chameleon decode pass (1 = round-1 kernel, 7 = write / verify / mailbox; default 7). */
+DENSITY_B200_API void density_b200_test_set_decode_impl(int k);
 /* Library version string. */
 DENSITY_B200_API const char* density_b200_version(void);
 

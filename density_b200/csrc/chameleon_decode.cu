@@ -378,43 +378,61 @@ struct Dec7Smem {
 };
 static_assert(sizeof(Dec7Smem) <= 227 * 1024, "decode pass shared memory");
 
-template <class SM>
-__device__ __forceinline__ void stage_tile7(SM& S, int buf, const uint8_t* __restrict__ in, const uint64_t* __restrict__ blk_off, uint64_t b0, uint64_t nblocks) {
-    const uint32_t tid = threadIdx.x;
-    if (tid < 64) {     // warps 0 and 1, whole warps
-        unsigned long long o = 0; uint32_t lo = 0, hi = 0; bool copied = false;
-        if (b0 + tid < nblocks) {
-            o = blk_off[b0 + tid];
-            copied = (o & BLK_COPY) != 0;
-            o &= ~BLK_COPY;
-            if (!copied) {
-                const uint8_t* p = in + o;
-                lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
-                o += 8;
-            }
-        }
-        S.boff[buf][tid] = o; S.bsig[buf][2 * tid] = lo; S.bsig[buf][2 * tid + 1] = hi;
-        const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, copied);
-        if ((tid & 31) == 0) S.bcopy[buf][tid >> 5] = cmask;
+// Staging of a tile's block offsets and signatures, three tiles deep in registers of threads 0..63 so that neither of the two
+// dependent global loads (offset -> signature) is waited for: at the top of tile t the values of tile t+1 (loads issued during tile
+// t-1) go to shared memory, the signature loads of tile t+2 are issued from its offsets (loaded during tile t-1) and the offset loads
+// of tile t+3 are issued.
+struct Stage7 {
+    unsigned long long o_sig;    // tile t+1 (then t+2): payload offset / copy flag as loaded
+    uint32_t lo, hi;             // its signature halves (in flight)
+    unsigned long long o_next;   // tile t+2 (then t+3): raw blk_off entry (in flight)
+};
+__device__ __forceinline__ unsigned long long stage7_load_off(const uint64_t* __restrict__ blk_off, uint64_t b, uint64_t nblocks) {
+    return b < nblocks ? __ldg(reinterpret_cast<const unsigned long long*>(blk_off) + b) : ~0ull;     // ~0: no such block
+}
+__device__ __forceinline__ void stage7_load_sig(const uint8_t* __restrict__ in, unsigned long long o, uint32_t& lo, uint32_t& hi) {
+    lo = 0; hi = 0;
+    if (o != ~0ull && !(o & BLK_COPY)) {
+        const uint8_t* p = in + o;
+        lo = ldu16(p) | (ldu16(p + 2) << 16); hi = ldu16(p + 4) | (ldu16(p + 6) << 16);
     }
+}
+__device__ __forceinline__ void stage7_commit(Dec7Smem& S, int buf, unsigned long long o, uint32_t lo, uint32_t hi) {
+    const uint32_t tid = threadIdx.x;     // < 64: warps 0 and 1, whole warps
+    const bool none = o == ~0ull;
+    const bool copied = !none && (o & BLK_COPY) != 0;
+    unsigned long long off = none ? 0ull : (o & ~BLK_COPY);
+    if (!none && !copied) off += 8;       // payload starts behind the signature; a copy-mode block is 64 raw quads at the block start
+    S.boff[buf][tid] = off; S.bsig[buf][2 * tid] = lo; S.bsig[buf][2 * tid + 1] = hi;
+    const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, copied);
+    if ((tid & 31) == 0) S.bcopy[buf][tid >> 5] = cmask;
+}
+// predicated 16-bit load without a branch: the loads of all sub-rows leave back to back (a branch per sub-row would make every
+// sub-row wait for its own load: 8 exposed HBM latencies per tile)
+__device__ __forceinline__ uint32_t ldu16_if(const uint8_t* p, bool pred) {
+    uint32_t v;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; mov.u32 %0, 0; @q ld.global.nc.u16 %0, [%1]; }" : "=r"(v) : "l"(p), "r"((uint32_t)pred));
+    return v;
 }
 template <bool WONLY>
 __device__ __forceinline__ void fetch_payload7(const Dec7Smem& S, int buf, const uint8_t* __restrict__ in, uint32_t nb_tile, uint32_t (&v)[D7_QPT]) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t a[D7_QPT], b[D7_QPT];
 #pragma unroll
     for (int j = 0; j < D7_QPT; ++j) {
         const uint32_t bl = warp * (D7_WQ / 64) + (j >> 1);
         const uint32_t k = (j & 1) * 32 + lane;
-        v[j] = 0;
-        if (bl < nb_tile) {
-            const uint32_t lo = S.bsig[buf][2 * bl], hi = S.bsig[buf][2 * bl + 1];
-            const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
-            const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
-            const uint8_t* p = in + S.boff[buf][bl] + 4 * k - 2 * before;
-            if (flag) { if (!WONLY) v[j] = ldu16(p); }
-            else v[j] = ldu16(p) | (ldu16(p + 2) << 16);
-        }
+        const bool in_tile = bl < nb_tile;
+        const uint32_t blc = in_tile ? bl : 0u;
+        const uint32_t lo = S.bsig[buf][2 * blc], hi = S.bsig[buf][2 * blc + 1];
+        const uint32_t flag = (((j & 1) ? hi : lo) >> lane) & 1u;
+        const uint32_t before = (j & 1) ? (__popc(lo) + __popc(hi & lanemask_lt())) : __popc(lo & lanemask_lt());
+        const uint8_t* p = in + S.boff[buf][blc] + 4 * k - 2 * before;
+        a[j] = ldu16_if(p, in_tile && !(WONLY && flag));        // MAP: the 16-bit hash (chameleon.rs:64); PLAIN: low half of the quad (:56)
+        b[j] = ldu16_if(p + 2, in_tile && !flag);               // PLAIN: high half
     }
+#pragma unroll
+    for (int j = 0; j < D7_QPT; ++j) v[j] = a[j] | (b[j] << 16);
 }
 
 // Fallback: the tile's writers and suspects in stream order by one warp.
@@ -498,7 +516,15 @@ cham_decode_pass7(const uint8_t* __restrict__ in, const uint64_t* __restrict__ b
     }
     __syncthreads();
     uint32_t nval[D7_QPT];
-    if (t_begin < t_end) stage_tile7(S, 0, in, blk_off, t_begin * 64, nblocks);
+    Stage7 sg; sg.o_sig = ~0ull; sg.lo = 0; sg.hi = 0; sg.o_next = ~0ull;
+    if (t_begin < t_end && tid < 64) {
+        const unsigned long long o0 = stage7_load_off(blk_off, t_begin * 64 + tid, nblocks);
+        uint32_t lo0, hi0;
+        stage7_load_sig(in, o0, lo0, hi0);
+        stage7_commit(S, 0, o0, lo0, hi0);
+        if (t_begin + 1 < t_end) { sg.o_sig = stage7_load_off(blk_off, (t_begin + 1) * 64 + tid, nblocks); stage7_load_sig(in, sg.o_sig, sg.lo, sg.hi); }
+        if (t_begin + 2 < t_end) sg.o_next = stage7_load_off(blk_off, (t_begin + 2) * 64 + tid, nblocks);
+    }
     __syncthreads();
     if (t_begin < t_end) fetch_payload7<WONLY>(S, 0, in, (uint32_t)((nblocks - t_begin * 64 < 64) ? (nblocks - t_begin * 64) : 64), nval);
 
@@ -507,7 +533,13 @@ cham_decode_pass7(const uint8_t* __restrict__ in, const uint64_t* __restrict__ b
         const uint32_t nb_tile = (uint32_t)((nblocks - b0 < 64) ? (nblocks - b0) : 64);
         const int cur = (int)((t - t_begin) & 1);
         const uint32_t buf = (uint32_t)cur;
-        if (t + 1 < t_end) stage_tile7(S, cur ^ 1, in, blk_off, b0 + 64, nblocks);
+        if (tid < 64) {
+            if (t + 1 < t_end) stage7_commit(S, cur ^ 1, sg.o_sig, sg.lo, sg.hi);          // tile t+1: loaded during tile t-1
+            sg.o_sig = sg.o_next;                                                           // tile t+2: its signatures leave now
+            sg.lo = 0; sg.hi = 0;
+            if (t + 2 < t_end) stage7_load_sig(in, sg.o_sig, sg.lo, sg.hi);
+            sg.o_next = (t + 3 < t_end) ? stage7_load_off(blk_off, (t + 3) * 64 + tid, nblocks) : ~0ull;   // tile t+3: its offsets leave now
+        }
 #pragma unroll
         for (int k = 0; k < D7_MB_SLOTS / 4 / D7_THREADS; ++k) S.mbcnt[buf ^ 1u][tid + k * D7_THREADS] = 0;
         if (tid < D7_SEC_SLOTS) S.seccnt[buf ^ 1u][tid] = 0;

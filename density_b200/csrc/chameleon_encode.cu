@@ -913,8 +913,28 @@ __device__ __forceinline__ void prot_walk(Protection& ps, const uint8_t* __restr
 //   state of segment s-1 differs from the incoming state it was last evaluated with; a chain of L consecutive segments with
 //   non-canonical seams settles after L rounds) -> in-order fix-up by one CTA if PROT_ROUNDS rounds were not enough
 //   -> compare the new copy map with the one the flags were computed under -> converged / commit.
-constexpr int PROT_ROUNDS = 48;
-constexpr int PI_THREADS = 256;
+constexpr int PROT_ROUNDS = 48, PROT_FAST_ROUNDS = 0;   // measured: the candidate evaluation first beats "a few relaxation rounds first" on text, mixed and noise
+constexpr int PI_THREADS = 1024;
+
+// Exact evaluation in one shot for ordinary data: the automaton state at a segment seam is (penalty, start, previous_incompressible)
+// with small penalty and start in practice (start halves every 16 blocks and grows by one per copy-mode episode: it hovers around 3-4
+// even on pure noise). So every segment is walked from EVERY candidate state (PC_NC of them), which gives its transfer table
+// candidate -> candidate (or PC_ESC when the walk ends outside the candidate set); the tables are composed per group of PC_GROUP
+// segments, the group tables in order by one thread from the canonical state, the true incoming states are handed back down, and
+// each segment is walked once more from its true state, now writing the copy map. No relaxation rounds, whatever the data. A true
+// path that meets PC_ESC (never seen) falls back to the relaxation below.
+constexpr uint32_t PC_NS = 10, PC_NP = 10, PC_NC = 2 * PC_NS * PC_NP, PC_ESC = 0xFFFFu, PC_GROUP = 128;
+__host__ __device__ __forceinline__ size_t prot_table_elems(uint64_t nseg) {     // u16 elements behind the 2 (nseg + 1) state words
+    const uint64_t ngrp = (nseg + PC_GROUP - 1) / PC_GROUP;
+    return (size_t)(2 * (ngrp + 2) + nseg * PC_NC + ngrp * PC_NC + 64);
+}
+__device__ __forceinline__ void pc_decode(uint32_t c, Protection& ps) {
+    ps.copy_penalty = c % PC_NP; ps.copy_penalty_start = (c / PC_NP) % PC_NS + 1u; ps.previous_incompressible = c / (PC_NP * PC_NS);
+}
+__device__ __forceinline__ uint32_t pc_encode(const Protection& ps) {
+    if (ps.copy_penalty >= PC_NP || ps.copy_penalty_start < 1u || ps.copy_penalty_start > PC_NS) return PC_ESC;
+    return (ps.previous_incompressible * PC_NS + (ps.copy_penalty_start - 1u)) * PC_NP + ps.copy_penalty;
+}
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nctas, unsigned int& epoch) {
     __syncthreads();
@@ -932,7 +952,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 __global__ void __launch_bounds__(PI_THREADS)
 prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* __restrict__ st, int it,
              uint8_t* __restrict__ inc, uint8_t* __restrict__ cm_old, uint8_t* __restrict__ cm_new,
-             uint32_t* __restrict__ in_state, uint32_t* __restrict__ out_state) {
+             uint32_t* __restrict__ in_state, uint32_t* __restrict__ out_state, uint16_t* __restrict__ ptab) {
     if (!gate_open(st)) return;                       // uniform over the grid: read before anybody modifies `converged`
     __shared__ uint32_t s_state[1024], s_in[1024];
     __shared__ uint8_t s_inc[PSEG], s_cm[PSEG];
@@ -949,9 +969,13 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
     if (gtid == 0) { st->relax_changed[0] = 0; st->relax_changed[1] = 0; st->iter_changed = 0; }
     grid_barrier(bar, gridDim.x, epoch);
 
-    // (2) relaxation rounds
+    // (2) phase 0: the candidate-state evaluation (2a) (PROT_FAST_ROUNDS relaxation rounds before it: 0); phase 1, only if that met
+    //     PC_ESC: relaxation rounds (segment s is re-evaluated whenever the outgoing state of segment s-1 changed)
     bool settled = false;
-    for (int round = 0; round < PROT_ROUNDS; ++round) {
+    int round = 0;
+    for (int phase = 0; phase < 2 && !settled; ++phase) {
+    const int limit = (phase == 0 && ptab) ? PROT_FAST_ROUNDS : PROT_ROUNDS;
+    for (; round < limit; ++round) {
         for (uint64_t s = gtid; s < nseg; s += gsz) {
             const uint32_t new_in = (s && round) ? __ldcg(&out_state[s - 1]) : (1u << 8);   // L2 read: written by other SMs during this kernel
             if (round > 0 && new_in == in_state[s]) continue;
@@ -972,6 +996,57 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
         if (gtid == 0) st->relax_changed[(round + 1) & 1] = 0;      // the flag of the next round (nobody reads it before the next barrier)
         grid_barrier(bar, gridDim.x, epoch);
     }
+    // (2a) candidate-state evaluation (see PC_NC above)
+    if (phase == 0 && !settled && ptab) {
+        const uint32_t ngrp = (nseg + PC_GROUP - 1) / PC_GROUP;
+        uint32_t* gin = reinterpret_cast<uint32_t*>(ptab);                   // incoming candidate of every group, then the final state
+        uint16_t* T = ptab + 2 * (ngrp + 2);
+        uint16_t* GT = T + (size_t)nseg * PC_NC;
+        for (uint64_t idx = gtid; idx < (uint64_t)nseg * PC_NC; idx += gsz) {
+            const uint64_t s = idx / PC_NC;
+            Protection ps; pc_decode((uint32_t)(idx % PC_NC), ps);
+            ps.counter = s * PSEG;
+            const uint64_t b1 = ((s + 1) * PSEG < nblocks) ? (s + 1) * PSEG : nblocks;
+            for (uint64_t b = s * PSEG; b < b1; ++b) {
+                if (ps.revert_to_copy()) ps.decay();
+                else ps.update(__ldcg(&inc[b]) != 0);
+            }
+            T[idx] = (uint16_t)pc_encode(ps);
+        }
+        grid_barrier(bar, gridDim.x, epoch);
+        for (uint64_t idx = gtid; idx < (uint64_t)ngrp * PC_NC; idx += gsz) {
+            const uint32_t g = (uint32_t)(idx / PC_NC);
+            uint32_t x = (uint32_t)(idx % PC_NC);
+            const uint32_t s1 = ((g + 1) * PC_GROUP < nseg) ? (g + 1) * PC_GROUP : nseg;
+            for (uint32_t s = g * PC_GROUP; s < s1 && x != PC_ESC; ++s) x = __ldcg(&T[(size_t)s * PC_NC + x]);
+            GT[idx] = (uint16_t)x;
+        }
+        grid_barrier(bar, gridDim.x, epoch);
+        if (gtid == 0) {
+            uint32_t x = 0;                                                  // canonical state: penalty 0, start 1, not incompressible
+            for (uint32_t g = 0; g < ngrp; ++g) { gin[g] = x; if (x != PC_ESC) x = __ldcg(&GT[(size_t)g * PC_NC + x]); }
+            gin[ngrp] = x;
+        }
+        grid_barrier(bar, gridDim.x, epoch);
+        if (__ldcg(&gin[ngrp]) != PC_ESC) {                                  // uniform over the grid
+            for (uint64_t g = gtid; g < ngrp; g += gsz) {
+                uint32_t x = __ldcg(&gin[g]);
+                const uint32_t s1 = ((g + 1) * PC_GROUP < nseg) ? (uint32_t)((g + 1) * PC_GROUP) : nseg;
+                for (uint32_t s = (uint32_t)g * PC_GROUP; s < s1; ++s) { in_state[s] = x; x = __ldcg(&T[(size_t)s * PC_NC + x]); }
+            }
+            grid_barrier(bar, gridDim.x, epoch);
+            for (uint64_t s = gtid; s < nseg; s += gsz) {
+                Protection ps; pc_decode(__ldcg(&in_state[s]), ps);
+                ps.counter = s * PSEG;
+                const uint64_t b1 = ((s + 1) * PSEG < nblocks) ? (s + 1) * PSEG : nblocks;
+                prot_walk(ps, inc, s * PSEG, b1, cm_new);
+            }
+            grid_barrier(bar, gridDim.x, epoch);
+            settled = true;
+        }
+    }
+
+    }   // phase
 
     // (3) pathologically long incompressible stretches: finish in order (one CTA; a stored result stands when it was computed
     //     from the true incoming state)
@@ -1397,7 +1472,7 @@ size_t cham_workspace_bytes(size_t nbytes, int nruns_max, ChamLayout* L) {
     L->sigw = take((ntiles * 64 * 2 + 64 + 256) * sizeof(uint32_t));   // + one 64-block tile: the flag pass works in 128-block tiles
     L->copymap = take(ntiles * 64 + 64 + 128);
     L->copymap2 = take(ntiles * 64 + 64 + 128);
-    L->seg_state = take((2 * (ntiles * 64 / PSEG + 2) + 64) * sizeof(uint32_t));
+    L->seg_state = take(prot_state_bytes(ntiles * 64 / PSEG + 2));
     L->incb = take(ntiles * 64 + 64);
     L->tile_bytes = take((ntiles + 1) * sizeof(uint32_t));
     L->tile_local = take((ntiles + 1) * sizeof(uint32_t));
@@ -1433,6 +1508,8 @@ static void launch_flag_pass(uint32_t nruns, cudaStream_t stream, const uint32_t
     else
         cham_flag_pass6<<<nruns, F6_THREADS, sizeof(Flag6Smem), stream>>>(in, nquads, ntiles, nruns, sigw, unres, unres_count, final_tab, copymap, gate);
 }
+
+size_t prot_state_bytes(uint64_t nseg_max) { return (2 * (nseg_max + 2) + 64) * sizeof(uint32_t) + prot_table_elems(nseg_max) * sizeof(uint16_t); }
 
 uint32_t cham_pick_runs(size_t nbytes, int num_sms) {
     const uint64_t nblocks = (nbytes + 255) / 256;
@@ -1534,7 +1611,7 @@ cudaError_t cham_phase2_rounds(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
             *launches += 3;
         }
         prot_iterate<<<num_ctas, PI_THREADS, 0, stream>>>(sigw, nbytes, nblocks, nseg, st, it, incb, copymap, copymap2,
-                                                          seg_state, seg_state + (nseg + 1));
+                                                          seg_state, seg_state + (nseg + 1), reinterpret_cast<uint16_t*>(seg_state + 2 * (nseg + 1)));
         ++*launches;
     }
     return cudaGetLastError();
@@ -1666,7 +1743,9 @@ cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, u
                                 cudaStream_t stream) {
     int ctas = num_sms > 0 ? num_sms : 1;
     if ((uint32_t)ctas > nseg) ctas = nseg ? (int)nseg : 1;       // small inputs: cheaper grid barriers
-    prot_iterate<<<ctas, PI_THREADS, 0, stream>>>(sigw_or_null, nbytes, nblocks, nseg, st, it, inc, cm_old, cm_new, in_state, out_state);
+    // the caller's state region is sized by prot_state_bytes(): the candidate tables live behind the 2 (nseg + 1) state words
+    prot_iterate<<<ctas, PI_THREADS, 0, stream>>>(sigw_or_null, nbytes, nblocks, nseg, st, it, inc, cm_old, cm_new, in_state, out_state,
+                                                  reinterpret_cast<uint16_t*>(out_state + (nseg + 1)));
     return cudaGetLastError();
 }
 cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint32_t* tile_local, uint64_t* group_total, uint64_t* group_off,

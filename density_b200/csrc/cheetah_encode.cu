@@ -664,7 +664,7 @@ static size_t chee_layout(size_t nbytes, uint32_t nruns, CheeLayout* L) {
     L->copymap = take(maxblocks + 64);
     L->copymap2 = take(maxblocks + 64);
     L->incb = take(maxblocks + 64);
-    L->seg_state = take((2 * (maxblocks / 256 + 2) + 64) * 4);
+    L->seg_state = take(prot_state_bytes(maxblocks / 256 + 2));
     L->ctx0 = take((size_t)nruns * 4 + 64);
     L->tile_bytes = take((ntiles + 1) * 4);
     L->tile_local = take((ntiles + 1) * 4);

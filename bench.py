@@ -402,6 +402,15 @@ def run_ours(args):
                 assert ok, "cheetah: parallel decode(encode(x)) != x"
             del d_o2
         del d_dec
+        # Chameleon encode of data on which the protection automaton fires (copy-mode blocks): 256 MiB of noise and of mixed text / binary
+        for kind, gen in (("noise", lambda k: synth.random_bytes(k, 5, device=dev)), ("mixed", lambda k: synth.synth_mixed(k, device=dev))):
+            nk = 256 << 20
+            d_k = gen(nk)
+            d_ok = torch.empty(density_b200.Chameleon.safe_encode_buffer_size(nk), dtype=torch.uint8, device=dev)
+            kms = timed(lambda: density_b200.encode_device("chameleon", d_k, d_ok, d_dsz), 3)
+            extra[f"chameleon_encode_{kind}_256MiB_GBps"] = nk / (kms * 1e-3) / 1e9
+            extra[f"chameleon_encode_{kind}_256MiB_ratio"] = nk / max(int(d_dsz.item()), 1)
+            del d_k, d_ok
         # config 1: Chameleon round trip on Silesia/dickens through the reference symbols (latency-bound on a GPU; reported, not optimised)
         dk = None
         for cand, label in ((os.path.join(ROOT, "oracle", "_ref", "dickens.txt"), "benches/data/dickens.txt (10,192,446 B)"),

@@ -913,7 +913,7 @@ __device__ __forceinline__ void prot_walk(Protection& ps, const uint8_t* __restr
 //   state of segment s-1 differs from the incoming state it was last evaluated with; a chain of L consecutive segments with
 //   non-canonical seams settles after L rounds) -> in-order fix-up by one CTA if PROT_ROUNDS rounds were not enough
 //   -> compare the new copy map with the one the flags were computed under -> converged / commit.
-constexpr int PROT_ROUNDS = 48, PROT_FAST_ROUNDS = 0;   // measured: the candidate evaluation first beats "a few relaxation rounds first" on text, mixed and noise
+constexpr int PROT_ROUNDS = 48, PROT_FAST_ROUNDS = 4;   // relaxation rounds before the candidate evaluation when only a few seams are not canonical
 constexpr int PI_THREADS = 1024;
 
 // Exact evaluation in one shot for ordinary data: the automaton state at a segment seam is (penalty, start, previous_incompressible)
@@ -966,11 +966,13 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
     if (sigw_g)   // Chameleon: derive the bits from the signatures; other codecs pass sigw_g == nullptr and fill `inc` themselves
         for (uint64_t b = gtid; b < nblocks; b += gsz)
             if (!(it && cm_old[b])) inc[b] = (nbytes - b * 256 >= 256) && (__popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]) <= 4);
-    if (gtid == 0) { st->relax_changed[0] = 0; st->relax_changed[1] = 0; st->iter_changed = 0; }
+    if (gtid == 0) { st->relax_changed[0] = 0; st->relax_changed[1] = 0; st->iter_changed = 0; st->pad2[0] = 0; }
     grid_barrier(bar, gridDim.x, epoch);
 
-    // (2) phase 0: the candidate-state evaluation (2a) (PROT_FAST_ROUNDS relaxation rounds before it: 0); phase 1, only if that met
-    //     PC_ESC: relaxation rounds (segment s is re-evaluated whenever the outgoing state of segment s-1 changed)
+    // (2) phase 0: round 0 evaluates every segment from the canonical state and counts the seams that are not canonical. None: done
+    //     (text). A few (bursts inside text): relaxation rounds (segment s is re-evaluated whenever the outgoing state of segment s-1
+    //     changed), at most PROT_FAST_ROUNDS. Many (mixed data, noise: a chain of L non-canonical seams needs L rounds), or not settled:
+    //     the candidate-state evaluation (2a). Phase 1, only if that met PC_ESC: the remaining relaxation rounds.
     bool settled = false;
     int round = 0;
     for (int phase = 0; phase < 2 && !settled; ++phase) {
@@ -987,8 +989,14 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
             in_state[s] = new_in;
             out_state[s] = prot_pack(ps);
             if (round > 0) st->relax_changed[round & 1] = 1;
+            else if (prot_pack(ps) != (1u << 8)) atomicAdd(&st->pad2[0], 1u);
         }
         grid_barrier(bar, gridDim.x, epoch);
+        if (round == 0 && phase == 0 && ptab) {
+            const unsigned int bad = *((volatile unsigned int*)&st->pad2[0]);      // uniform over the grid
+            if (bad == 0) { settled = true; break; }
+            if (bad > 8u) { round = 1; break; }                                     // straight to the candidate evaluation
+        }
         if (round > 0) {
             const bool changed = *((volatile unsigned int*)&st->relax_changed[round & 1]) != 0;
             if (!changed) { settled = true; break; }
@@ -1007,7 +1015,17 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
             Protection ps; pc_decode((uint32_t)(idx % PC_NC), ps);
             ps.counter = s * PSEG;
             const uint64_t b1 = ((s + 1) * PSEG < nblocks) ? (s + 1) * PSEG : nblocks;
-            for (uint64_t b = s * PSEG; b < b1; ++b) {
+            uint64_t b = s * PSEG;
+            for (; b + 16 <= b1; b += 16) {                       // 16 incompressible bytes per L2 load (segments start 256-byte aligned)
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(inc + b));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (ps.revert_to_copy()) ps.decay();
+                    else ps.update(((w[k >> 2] >> ((k & 3) * 8)) & 0xFFu) != 0);
+                }
+            }
+            for (; b < b1; ++b) {
                 if (ps.revert_to_copy()) ps.decay();
                 else ps.update(__ldcg(&inc[b]) != 0);
             }
@@ -1509,6 +1527,12 @@ static void launch_flag_pass(uint32_t nruns, cudaStream_t stream, const uint32_t
         cham_flag_pass6<<<nruns, F6_THREADS, sizeof(Flag6Smem), stream>>>(in, nquads, ntiles, nruns, sigw, unres, unres_count, final_tab, copymap, gate);
 }
 
+static cudaError_t prot_iterate_coop(int ctas, cudaStream_t stream, const uint32_t* sigw, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* st, int it,
+                                     uint8_t* inc, uint8_t* cm_old, uint8_t* cm_new, uint32_t* in_state, uint32_t* out_state, uint16_t* ptab) {
+    void* args[] = {&sigw, &nbytes, &nblocks, &nseg, &st, &it, &inc, &cm_old, &cm_new, &in_state, &out_state, &ptab};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(prot_iterate), dim3((unsigned)ctas), dim3(PI_THREADS), args, 0, stream);
+}
+
 size_t prot_state_bytes(uint64_t nseg_max) { return (2 * (nseg_max + 2) + 64) * sizeof(uint32_t) + prot_table_elems(nseg_max) * sizeof(uint16_t); }
 
 uint32_t cham_pick_runs(size_t nbytes, int num_sms) {
@@ -1610,8 +1634,11 @@ cudaError_t cham_phase2_rounds(const uint8_t* d_in, size_t nbytes, uint8_t* ws, 
                                                              reinterpret_cast<uint32_t*>(ws + L.carry), ntiles, nruns, sigw, st);
             *launches += 3;
         }
-        prot_iterate<<<num_ctas, PI_THREADS, 0, stream>>>(sigw, nbytes, nblocks, nseg, st, it, incb, copymap, copymap2,
-                                                          seg_state, seg_state + (nseg + 1), reinterpret_cast<uint16_t*>(seg_state + 2 * (nseg + 1)));
+        {   // cooperative launch: the software grid barriers need every CTA resident (the runtime checks it instead of a hang)
+            cudaError_t le = prot_iterate_coop(num_ctas, stream, sigw, nbytes, nblocks, nseg, st, it, incb, copymap, copymap2, seg_state, seg_state + (nseg + 1),
+                                               reinterpret_cast<uint16_t*>(seg_state + 2 * (nseg + 1)));
+            if (le != cudaSuccess) return le;
+        }
         ++*launches;
     }
     return cudaGetLastError();
@@ -1744,9 +1771,9 @@ cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, u
     int ctas = num_sms > 0 ? num_sms : 1;
     if ((uint32_t)ctas > nseg) ctas = nseg ? (int)nseg : 1;       // small inputs: cheaper grid barriers
     // the caller's state region is sized by prot_state_bytes(): the candidate tables live behind the 2 (nseg + 1) state words
-    prot_iterate<<<ctas, PI_THREADS, 0, stream>>>(sigw_or_null, nbytes, nblocks, nseg, st, it, inc, cm_old, cm_new, in_state, out_state,
-                                                  reinterpret_cast<uint16_t*>(out_state + (nseg + 1)));
-    return cudaGetLastError();
+    return prot_iterate_coop(ctas, stream, sigw_or_null, nbytes, nblocks, nseg, st, it, inc, cm_old, cm_new, in_state, out_state,
+                             reinterpret_cast<uint16_t*>(out_state + (nseg + 1)));
+
 }
 cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint32_t* tile_local, uint64_t* group_total, uint64_t* group_off,
                               uint32_t ngroups, Status* st, uint64_t cap, uint64_t* d_out_size, cudaStream_t stream) {

@@ -128,6 +128,67 @@ def _same_bucket_pair():
         seen[h] = q
 
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", [6, 1])
+def test_chameleon_runs_of_equal_quads_and_mailbox_overflow(torch_cuda, codecs, impl):
+    """Round-2 flag pass (write / verify / mailbox): runs of equal quads of every length up to several tiles (one mailbox entry per run:
+    the run is dropped at deposit time), runs cut by a different quad of the same bucket, 5 - 40 quads of one bucket that are NOT a run
+    (main mailbox -> overflow mailboxes -> in-order replay of the tile), all inside text so that most blocks stay compressible; the
+    round-1 kernel must agree (impl 1)."""
+    torch = torch_cuda
+    import density_b200
+    from density_b200 import synth
+    rng = np.random.default_rng(5)
+    q1, q2 = _same_bucket_pair()
+    text = synth.synth_text(6 << 20).numpy().view(np.uint32).copy()
+    pieces, pos = [], 0
+    lens = [1, 2, 3, 5, 31, 32, 33, 64, 255, 256, 257, 1000, 4095, 4096, 4097, 9000]
+    vals = [0, 0xFFFFFFFF, 0x20202020, q1, q2, 0x80000000, 1]
+    k = 0
+    while pos + 20000 < text.size:
+        step = int(rng.integers(3000, 20000))
+        pieces.append(text[pos:pos + step]); pos += step
+        L = lens[k % len(lens)]; v = vals[k % len(vals)]
+        if k % 3 == 0:
+            pieces.append(np.full(L, v, dtype=np.uint32))                                   # a plain run
+        elif k % 3 == 1:
+            run = np.full(L, q1, dtype=np.uint32); run[L // 2] = q2                          # a run cut by a quad of the same bucket
+            pieces.append(run)
+        else:
+            m = 5 + (k % 36)                                                                 # m dirty members of one bucket, no two adjacent equal
+            burst = np.empty(2 * m, dtype=np.uint32); burst[0::2] = q1 if (k & 1) else q2; burst[1::2] = text[pos:pos + m]
+            burst[0::4] = q2 if (k & 1) else q1
+            pieces.append(burst)
+        k += 1
+    data = np.concatenate(pieces).view(np.uint8)[:-1]
+    want = oracle.encode("chameleon", data)
+    lib = density_b200.load()
+    lib.density_b200_test_set_flag_impl(impl)
+    try:
+        for path in (0, 1):
+            d_in = torch.from_numpy(data.copy()).cuda()
+            d_out = torch.zeros(codecs["chameleon"].safe_encode_buffer_size(data.size) + 64, dtype=torch.uint8, device="cuda")
+            d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+            density_b200.encode_device("chameleon", d_in, d_out, d_sz, path=path)
+            torch.cuda.synchronize()
+            n = int(d_sz.item())
+            if path == 1 and n == 0:
+                continue          # path 1 = parallel only: gives up (size 0) when the copy map does not settle; path 0 must still be exact
+            assert n == want.size and (d_out[:n].cpu().numpy() == want).all(), (impl, path)
+        # and back through the decoder (both decode pass kernels)
+        for dimpl in (7, 1):
+            lib.density_b200_test_set_decode_impl(dimpl)
+            d_enc = torch.from_numpy(want.copy()).cuda()
+            d_dec = torch.zeros(data.size + 64, dtype=torch.uint8, device="cuda")
+            density_b200.decode_device("chameleon", d_enc, want.size, d_dec, d_sz, path=0)
+            torch.cuda.synchronize()
+            assert int(d_sz.item()) == data.size and (d_dec[:data.size].cpu().numpy() == data).all(), dimpl
+    finally:
+        lib.density_b200_test_set_flag_impl(6)
+        lib.density_b200_test_set_decode_impl(7)
+
+
 @pytest.mark.parametrize("path", [0, 1, 2])
 def test_chameleon_adversarial_same_bucket_alternation(torch_cuda, codecs, path):
     """Thousands of interleaving quads in ONE hash bucket per tile (class-list overflow -> sequential in-tile fallback),

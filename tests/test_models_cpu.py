@@ -141,3 +141,147 @@ def test_planned_lion_decoder_model_round_trips(name):
     enc = oracle.encode("lion", data)
     got, ncopy, produced = D.decode(enc, data.size, nruns=3)
     assert produced == data.size and (got == data).all()
+
+
+def _flag_cases():
+    from tools import proto_tile_protocol_v6 as m6
+    d = np.fromfile(os.path.join(ROOT, "tests", "golden", "dickens_200k.bin"), np.uint8)
+    rng = np.random.default_rng(9)
+    text = d[:160000].view(np.uint32).copy()
+    # two quads of one bucket
+    seen, q = {}, 0x12345678
+    while True:
+        q = (q * 1103515245 + 12345) & 0xFFFFFFFF
+        hh = ((q * m6.M) & 0xFFFFFFFF) >> 16
+        if hh in seen and seen[hh] != q:
+            q1, q2 = seen[hh], q
+            break
+        seen[hh] = q
+    runs = []
+    pos = 0
+    for k, L in enumerate([1, 2, 3, 31, 32, 33, 255, 4096, 4097, 700, 5, 64]):
+        runs.append(text[pos:pos + 1500]); pos += 1500
+        v = [0, 0xFFFFFFFF, 0x20202020, q1, q2][k % 5]
+        r = np.full(L, v, np.uint32)
+        if k % 2 and L > 2:
+            r[L // 2] = q2 if v != q2 else q1           # a run cut by another quad (of the same bucket for q1 / q2)
+        runs.append(r)
+    burst = np.empty(80, np.uint32); burst[0::2] = q1; burst[1::2] = text[:40]; burst[0::4] = q2      # 40 members of one bucket, not a run
+    return {
+        "dickens": text,
+        "noise": rng.integers(0, 2 ** 32, 20000, dtype=np.uint32),
+        "low": rng.integers(0, 4, 30000, dtype=np.uint32) * 0x01010101,
+        "runs": np.concatenate(runs + [text[pos:pos + 3000]]),
+        "pileup": np.concatenate([text[:5000], burst, text[5000:9000], np.tile(np.array([q1, q2], np.uint32), 300), text[9000:12000]]),
+        "zeros": np.zeros(9000, np.uint32),
+    }
+
+
+@pytest.mark.parametrize("name", ["dickens", "noise", "low", "runs", "pileup", "zeros"])
+def test_write_verify_mailbox_tile_protocol_equals_the_in_order_walk(name):
+    """cham_flag_pass6: racy publish, verify by re-reading, dirty members resolved through per-bucket mailboxes by
+    record index, runs of equal quads dropped, overflow mailboxes, in-order replay of a tile whose mailboxes overflow — for ANY winner
+    of the racy publishes the flags, the first touches and the final dictionary are those of chameleon.rs:86-101."""
+    from tools import proto_tile_protocol_v6 as m6
+    q = _flag_cases()[name]
+    want, want_tab = m6.reference_flags(q)
+    for seed in (1, 2, 3):
+        stats = {}
+        got, tab, touched = m6.flag_pass(q, seed=seed, stats=stats)
+        assert (got == want).all(), (name, seed, int((got != want).sum()))
+        assert {int(b): int(tab[b]) for b in np.flatnonzero(touched)} == want_tab
+        if name == "pileup":
+            assert stats["overflow"] >= 1          # the replay path is part of what is checked
+
+
+def _candidate_copy_map(inc, PSEG=256, GROUP=8, NS=10, NP=10):
+    """Model of prot_iterate's candidate-state evaluation (chameleon_encode.cu, PC_NC): transfer table per segment over the candidate
+    incoming states, composed per group and in order at the top, true states handed back down, final walk. Returns the copy map, or
+    None when the true path leaves the candidate set (the kernel then falls back to the relaxation)."""
+    nb = inc.size
+    nseg = (nb + PSEG - 1) // PSEG
+    NC, ESC = 2 * NS * NP, -1
+
+    def dec(c, counter):
+        return _Protection(c % NP, (c // NP) % NS + 1, bool(c // (NP * NS)), counter)
+
+    def enc(ps):
+        if ps.penalty >= NP or ps.start < 1 or ps.start > NS:
+            return ESC
+        return (int(ps.prev) * NS + (ps.start - 1)) * NP + ps.penalty
+
+    def walk(ps, s, cm=None):
+        for b in range(s * PSEG, min((s + 1) * PSEG, nb)):
+            if ps.revert_to_copy():
+                if cm is not None:
+                    cm[b] = 1
+                ps.penalty = (ps.penalty - 1) & 0xFF          # decay(), protection_state.rs:29-35
+                if ps.penalty == 0:
+                    ps.start = (ps.start + 1) & 0xFF
+            else:
+                if cm is not None:
+                    cm[b] = 0
+                ps.update(bool(inc[b]))
+        return ps
+
+    T = [[enc(walk(dec(c, s * PSEG), s)) for c in range(NC)] for s in range(nseg)]
+    ngrp = (nseg + GROUP - 1) // GROUP
+    GT = []
+    for g in range(ngrp):
+        row = []
+        for c in range(NC):
+            x = c
+            for s in range(g * GROUP, min((g + 1) * GROUP, nseg)):
+                if x != ESC:
+                    x = T[s][x]
+            row.append(x)
+        GT.append(row)
+    gin, x = [], 0
+    for g in range(ngrp):
+        gin.append(x)
+        if x != ESC:
+            x = GT[g][x]
+    if x == ESC:
+        return None
+    cm = np.zeros(nb, np.uint8)
+    for g in range(ngrp):
+        x = gin[g]
+        for s in range(g * GROUP, min((g + 1) * GROUP, nseg)):
+            walk(dec(x, s * PSEG), s, cm)
+            x = T[s][x]
+    return cm
+
+
+@pytest.mark.parametrize("kind", ["noise", "bursts", "alternating", "quiet"])
+def test_candidate_state_evaluation_of_the_protection_automaton(kind):
+    """prot_iterate (Protection): walking every segment from every candidate incoming state and composing the transfer
+    tables gives the copy map of the in-order automaton (codec.rs:35-37,68; protection_state.rs:18-47) on any incompressible-bit
+    sequence whose seam states stay inside the candidate set — noise (every block incompressible) included."""
+    rng = np.random.default_rng(21)
+    nb = 20000
+    if kind == "noise":
+        inc = np.ones(nb, bool)
+    elif kind == "bursts":
+        inc = np.zeros(nb, bool)
+        for _ in range(40):
+            a = int(rng.integers(0, nb - 600)); inc[a:a + int(rng.integers(2, 600))] = True
+    elif kind == "alternating":
+        inc = rng.random(nb) < 0.6
+    else:
+        inc = rng.random(nb) < 0.02
+        inc[1:] &= ~inc[:-1]
+    want = np.zeros(nb, np.uint8)
+    ps = _Protection()
+    for b in range(nb):
+        if ps.revert_to_copy():
+            want[b] = 1
+            ps.penalty = (ps.penalty - 1) & 0xFF
+            if ps.penalty == 0:
+                ps.start = (ps.start + 1) & 0xFF
+        else:
+            ps.update(bool(inc[b]))
+    got = _candidate_copy_map(inc, PSEG=64, GROUP=8)
+    assert got is not None, "the true path left the candidate set"
+    assert (got == want).all()
+    if kind == "quiet":
+        assert want.sum() == 0

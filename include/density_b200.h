@@ -52,6 +52,9 @@ DENSITY_B200_API size_t cheetah_decode(const uint8_t* input, size_t input_size, 
 DENSITY_B200_API size_t cheetah_safe_encode_buffer_size(size_t size);
 
 DENSITY_B200_API size_t lion_encode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
+/* PERFORMANCE LIMIT: lion_decode runs on the exact in-order device kernel (one thread, ~10-20 MB/s): no parallel formulation of the
+   5-deep move-to-front prediction lists that beats in-order is known. Results are bit-exact; for streams
+   beyond a few MiB the reference's CPU decoder is the faster choice for this one symbol. All other eight symbols run parallel kernels. */
 DENSITY_B200_API size_t lion_decode(const uint8_t* input, size_t input_size, uint8_t* output, size_t output_size);
 DENSITY_B200_API size_t lion_safe_encode_buffer_size(size_t size);
 
@@ -195,6 +198,8 @@ DENSITY_B200_API void density_b200_test_set_stage_rounds(int k);
 DENSITY_B200_API void density_b200_test_set_flag_impl(int k);
 /* Same for the Chameleon decode pass (1 = round-1 kernel, 7 = write / verify / mailbox; default 7). */
 DENSITY_B200_API void density_b200_test_set_decode_impl(int k);
+/* Same for Cheetah's prediction pass (1 = run-parallel walk of HBM tables, 6 = shared-memory table in two half-context sweeps; default 6). */
+DENSITY_B200_API void density_b200_test_set_cheetah_p_impl(int k);
 /* Library version string. */
 DENSITY_B200_API const char* density_b200_version(void);
 

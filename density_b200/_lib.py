@@ -47,7 +47,6 @@ _SIGS = {
     "density_b200_test_set_stage_rounds": (None, [ctypes.c_int]),
     "density_b200_test_set_flag_impl": (None, [ctypes.c_int]),
     "density_b200_test_set_decode_impl": (None, [ctypes.c_int]),
-    "density_b200_test_set_cheetah_p_impl": (None, [ctypes.c_int]),
     "density_b200_shutdown": (None, []),
     "density_b200_version": (ctypes.c_char_p, []),
 }

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdensity_b200.so")
-SOURCES = ["api.cu", "chameleon_encode.cu", "chameleon_decode.cu", "cheetah_encode.cu", "cheetah_p6.cu", "cl_decode.cu", "scalar_codec.cu"]
+SOURCES = ["api.cu", "chameleon_encode.cu", "chameleon_decode.cu", "cheetah_encode.cu", "cl_decode.cu", "scalar_codec.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",

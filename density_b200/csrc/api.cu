@@ -937,7 +937,6 @@ void density_b200_test_set_stage_rounds(int k) { g_chee_stage_rounds = (k >= 1 &
 /* test / timing hook: which Chameleon flag pass kernel runs (1 = round-1 class protocol, 6 = write / verify / replay, the default) */
 void density_b200_test_set_flag_impl(int k) { g_cham_flag_impl = (k == 1) ? 1 : 6; }
 void density_b200_test_set_decode_impl(int k) { g_cham_decode_impl = (k == 1) ? 1 : 7; }
-void density_b200_test_set_cheetah_p_impl(int k) { g_chee_pass_p_impl = (k == 1) ? 1 : 6; }
 
 const char* density_b200_version(void) { return "density_b200 0.1.0 (sm_100a)"; }
 

@@ -627,7 +627,6 @@ __global__ void chee_chain_gate(Status* __restrict__ st, const Status* __restric
 
 using namespace chee;
 
-int g_chee_pass_p_impl = 6;    // 1: run-parallel walk of HBM tables (round 1), 6: shared-memory table, two half-context sweeps
 int g_chee_stage_rounds = 7;   // rounds per stage of the copy-map iteration (7 = all; tests lower it, see density_b200_test_set_stage_rounds)
 
 struct CheeLayout {
@@ -685,13 +684,7 @@ size_t chee_workspace_bytes(size_t nbytes, int num_sms) {
 // 0 = pass-P entries, 1 = Lion's undecided-access indices (untagged), 2 = pass-C entries.
 size_t chee_tables_bytes(int alg, int region, size_t nbytes, int num_sms) {
     const size_t per = region == 0 ? (alg == ALG_LION ? 32 : 16) : region == 1 ? (alg == ALG_LION ? 32 : 0) : 16;
-    size_t bytes = (size_t)chee_pick_runs(nbytes, num_sms) * 65536 * per;
-    if (region == 0 && alg != ALG_LION) {       // also the scratch of the shared-memory pass P (needs no zeroing, never tagged)
-        const uint64_t ntiles = ((nbytes + 127) / 128 + TILE_B - 1) / TILE_B;
-        const size_t need = chee_p6_scratch_bytes(chee_p6_runs(ntiles ? ntiles : 1, num_sms));
-        if (bytes < need) bytes = need;
-    }
-    return bytes;
+    return (size_t)chee_pick_runs(nbytes, num_sms) * 65536 * per;
 }
 
 // Enqueue the parallel Cheetah / Lion encode. *d_converged (device u32) != 0 afterwards means d_out / d_out_size hold the result;
@@ -738,15 +731,9 @@ cudaError_t chee_encode_parallel(int alg, const uint8_t* d_in, size_t nbytes, ui
             chee_fold_c<<<65536 / 128, 128, 0, stream>>>(in32, runs, st, entC, epoch, Ab, Bb);
             lion_tile_sizes<<<(nt + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, mask, nb, nblk, nt, 0, st, incb, tile_bytes);
         } else {
-            if (g_chee_pass_p_impl == 6) {     // prediction table in shared memory, two half-context sweeps (cheetah_p6.cu)
-                cudaError_t pe = chee_pass_p6_launch(in32, nq, nt, mask, st, Pb, tables[0], num_sms, stream, launches);
-                if (pe != cudaSuccess) return pe;
-                *launches -= 3;
-            } else {
-                chee_ctx0<<<(runs + 127) / 128, 128, 0, stream>>>(in32, nq, mask, runs, nt, st, ctx0);
-                chee_pass_p<<<run_ctas, RP_WARPS * 32, 0, stream>>>(in32, nq, nstep, mask, runs, nt, st, ctx0, entP, epoch, Pb);
-                chee_fold_p<<<65536 / 128, 128, 0, stream>>>(in32, runs, st, entP, epoch, Pb);
-            }
+            chee_ctx0<<<(runs + 127) / 128, 128, 0, stream>>>(in32, nq, mask, runs, nt, st, ctx0);
+            chee_pass_p<<<run_ctas, RP_WARPS * 32, 0, stream>>>(in32, nq, nstep, mask, runs, nt, st, ctx0, entP, epoch, Pb);
+            chee_fold_p<<<65536 / 128, 128, 0, stream>>>(in32, runs, st, entP, epoch, Pb);
             chee_pass_c<1><<<run_ctas, RP_WARPS * 32, 0, stream>>>(in32, nq, nstep, nblk, mask, runs, nt, st, Pb, entC, epoch, Ab, Bb);
             chee_fold_c<<<65536 / 128, 128, 0, stream>>>(in32, runs, st, entC, epoch, Ab, Bb);
             chee_tile_sizes<<<(nt + 7) / 8, 256, 0, stream>>>(Pb, Ab, Bb, mask, nb, nblk, nt, 0, st, incb, tile_bytes);

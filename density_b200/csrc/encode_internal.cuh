@@ -44,14 +44,7 @@ cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, u
 cudaError_t scan_tiles_launch(const uint32_t* tile_bytes, uint32_t ntiles, uint32_t* tile_local, uint64_t* group_total, uint64_t* group_off,
                               uint32_t ngroups, Status* st, uint64_t cap, uint64_t* d_out_size, cudaStream_t stream);
 
-// cheetah_p6.cu (Cheetah pass P with the prediction table in shared memory)
-struct Status;
-size_t chee_p6_scratch_bytes(uint32_t nruns);
-uint32_t chee_p6_runs(uint64_t ntiles, int num_sms);
-cudaError_t chee_pass_p6_launch(const uint32_t* in, uint64_t nquads, uint64_t ntiles, const uint8_t* copymap, const Status* gate, uint32_t* Pbits,
-                                uint8_t* scratch, int num_sms, cudaStream_t stream, uint64_t* launches);
 // cheetah_encode.cu
-extern int g_chee_pass_p_impl;
 extern int g_chee_stage_rounds;
 size_t chee_workspace_bytes(size_t nbytes, int num_sms);
 size_t chee_tables_bytes(int alg, int region, size_t nbytes, int num_sms);

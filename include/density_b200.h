@@ -198,8 +198,6 @@ DENSITY_B200_API void density_b200_test_set_stage_rounds(int k);
 DENSITY_B200_API void density_b200_test_set_flag_impl(int k);
 /* Same for the Chameleon decode pass (1 = round-1 kernel, 7 = write / verify / mailbox; default 7). */
 DENSITY_B200_API void density_b200_test_set_decode_impl(int k);
-/* Same for Cheetah's prediction pass (1 = run-parallel walk of HBM tables, 6 = shared-memory table in two half-context sweeps; default 6). */
-DENSITY_B200_API void density_b200_test_set_cheetah_p_impl(int k);
 /* Library version string. */
 DENSITY_B200_API const char* density_b200_version(void);
 

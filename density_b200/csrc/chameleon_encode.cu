@@ -1141,6 +1141,7 @@ __global__ void cham_tile_sizes(const uint32_t* __restrict__ sigw_g, const uint8
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= ntiles) return;
+    if (use_copymap_if_nonquiet && !check_quiet && !status->nonquiet) return;   // quiet input: the sizes of the first pass stand
     const bool use_cm = copymap && (!use_copymap_if_nonquiet || status->nonquiet);
     uint32_t sum = 0, incm[2];
 #pragma unroll

@@ -285,3 +285,26 @@ def test_candidate_state_evaluation_of_the_protection_automaton(kind):
     assert (got == want).all()
     if kind == "quiet":
         assert want.sum() == 0
+
+
+@pytest.mark.parametrize("name", ["dickens", "noise", "low", "runs", "pileup", "zeros"])
+def test_decode_mark_map_mailbox_protocol_equals_the_in_order_decoder(name):
+    """cham_decode_pass7: hashed mark map (false positives only make suspects), writers-only mailboxes, the writer
+    without a successor leaves the bucket's value, in-order replay of an overflowing tile: the decoded quads and the final dictionary
+    are those of chameleon.rs:55-68 on the flag / payload sequence the in-order ENCODER produces for the same quads."""
+    from tools import proto_tile_protocol_v6 as m6
+    q = _flag_cases()[name]
+    flags, _ = m6.reference_flags(q)
+    # the encoder's view with a zero-initialised dictionary: first touches are hits only for quad 0 in bucket 0 (chameleon.rs:41,89-91)
+    h, _f = m6.hf(q)
+    hit = (flags == 1) | ((flags == 2) & (q == 0))
+    is_plain = ~hit
+    payload = np.where(is_plain, q.astype(np.uint64), h.astype(np.uint64))
+    want, want_dic = m6.decode_reference(is_plain, payload)
+    assert (want == q).all()                                        # the in-order decoder inverts the in-order encoder
+    stats = {}
+    got, dic = m6.decode_pass(is_plain, payload, stats=stats)
+    assert (got == want).all(), (name, int((got != want).sum()))
+    assert dic == want_dic
+    if name == "pileup":
+        assert stats["overflow"] >= 1

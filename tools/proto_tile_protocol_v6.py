@@ -123,3 +123,94 @@ def flag_pass(q, seed=1, stats=None):
             tab = newtab
         out[t0:t0 + n] = flags
     return out, tab, touched
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Decode side: `cham_decode_pass7` (chameleon_decode.cu). A tile's quads are writers (PLAIN: value in the stream, written to the
+# dictionary at hash(value)) or readers (MAP: 16-bit hash in the stream, value = the latest PLAIN quad of that bucket, 0 if none).
+#   A  readers read the pre-tile dictionary            B  writers store their fingerprint (racy) and raise a byte of a HASHED mark map
+#   C  a reader whose mark byte is clear is final (no writer of its bucket in this tile); the others are suspects
+#   D  a suspect takes the writer with the largest smaller stream index in its bucket (mailboxes hold writers only), else its pre-tile
+#      value; the writer without a successor leaves the bucket's final value; mailbox overflow => in-order replay of the tile
+MARK_N = 8192
+
+
+def decode_reference(is_plain, payload):
+    """In order: payload = quad for PLAIN, hash for MAP. Returns the quads."""
+    d = {}
+    out = np.zeros(is_plain.size, np.uint64)
+    for i in range(is_plain.size):
+        if is_plain[i]:
+            q = int(payload[i])
+            d[(q * M & 0xFFFFFFFF) >> 16] = q
+            out[i] = q
+        else:
+            out[i] = d.get(int(payload[i]), 0)
+    return out, d
+
+
+def decode_pass(is_plain, payload, seed=1, stats=None):
+    rng = np.random.default_rng(seed)
+    dic = {}                                   # bucket -> quad (the kernel keeps fingerprints; quad_from_hf is a bijection per bucket)
+    out = np.zeros(is_plain.size, np.uint64)
+    for t0 in range(0, is_plain.size, TILE):
+        pl, pay = is_plain[t0:t0 + TILE], payload[t0:t0 + TILE]
+        n = pl.size
+        hk = np.where(pl, ((pay.astype(np.uint64) * M) & 0xFFFFFFFF) >> 16, pay).astype(np.int64)
+        pre = [dic.get(int(hk[i])) for i in range(n)]              # phase A (readers)
+        widx = np.flatnonzero(pl)
+        mark = np.zeros(MARK_N, bool)
+        mark[hk[widx] & (MARK_N - 1)] = True                       # phase B (the racy stores themselves are never read back by the model:
+        #                                                            a suspect never trusts the dictionary, a clean reader's bucket is unwritten)
+        res = np.zeros(n, np.uint64)
+        suspects = []
+        for i in range(n):                                          # phase C
+            if pl[i]:
+                res[i] = pay[i]
+            elif not mark[int(hk[i]) & (MARK_N - 1)]:
+                res[i] = pre[i] if pre[i] is not None else 0
+            else:
+                suspects.append(i)
+        recs = sorted(list(widx) + suspects)                        # record index order == stream order
+        ridx = {i: k for k, i in enumerate(recs)}
+        mb, sec, overflow = {}, {}, False
+        for i in widx:
+            slot = int(hk[i]) & (MB_SLOTS - 1)
+            lst = mb.setdefault(slot, [])
+            if len(lst) < MB_CAP:
+                lst.append(ridx[i])
+            else:
+                l2 = sec.setdefault(slot & (SEC_SLOTS - 1), [])
+                if len(l2) < SEC_CAP:
+                    l2.append(ridx[i])
+                else:
+                    overflow = True
+        if stats is not None:
+            stats["overflow"] = stats.get("overflow", 0) + int(overflow)
+            stats["suspects"] = stats.get("suspects", 0) + len(suspects)
+        if overflow:                                                # d7_replay: records in order, "written so far in this tile" bitmap
+            seen = {}
+            for i in recs:
+                b = int(hk[i])
+                if pl[i]:
+                    seen[b] = int(pay[i])
+                else:
+                    res[i] = seen[b] if b in seen else (pre[i] if pre[i] is not None else 0)
+            dic.update(seen)
+        else:
+            for i in recs:                                          # phase D
+                b = int(hk[i])
+                slot = b & (MB_SLOTS - 1)
+                cand = list(mb.get(slot, []))
+                if len(mb.get(slot, [])) >= MB_CAP:
+                    cand += sec.get(slot & (SEC_SLOTS - 1), [])
+                same = [c for c in cand if int(hk[recs[c]]) == b]
+                k = ridx[i]
+                if pl[i]:
+                    if not any(c > k for c in same):
+                        dic[b] = int(pay[i])
+                else:
+                    lower = [c for c in same if c < k]
+                    res[i] = int(pay[recs[max(lower)]]) if lower else (pre[i] if pre[i] is not None else 0)
+        out[t0:t0 + n] = res
+    return out, dic

@@ -938,6 +938,14 @@ void density_b200_test_set_stage_rounds(int k) { g_chee_stage_rounds = (k >= 1 &
 void density_b200_test_set_flag_impl(int k) { g_cham_flag_impl = (k == 1) ? 1 : 6; }
 void density_b200_test_set_decode_impl(int k) { g_cham_decode_impl = (k == 1) ? 1 : 7; }
 
+/* diagnostic: the last copy-map iteration on the current device, per fixed-point round {first block whose copy status changed (~0: none),
+   number of such blocks}; 16 rounds x 2 values (synchronises) */
+int density_b200_prot_debug(uint64_t* out32) {
+    if (!out32) return DENSITY_B200_EARG;
+    if (cudaDeviceSynchronize() != cudaSuccess) return DENSITY_B200_ECUDA;
+    return prot_debug_read(reinterpret_cast<unsigned long long*>(out32)) == cudaSuccess ? DENSITY_B200_OK : DENSITY_B200_ECUDA;
+}
+
 const char* density_b200_version(void) { return "density_b200 0.1.0 (sm_100a)"; }
 
 }  // extern "C"

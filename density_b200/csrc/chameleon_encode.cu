@@ -949,6 +949,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __syncthreads();
 }
 
+// diagnostics of the last iteration: per fixed-point round {first block whose copy status changed, number of such blocks}
+__device__ unsigned long long g_prot_dbg[16][2];
+
 __global__ void __launch_bounds__(PI_THREADS)
 prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* __restrict__ st, int it,
              uint8_t* __restrict__ inc, uint8_t* __restrict__ cm_old, uint8_t* __restrict__ cm_new,
@@ -967,6 +970,7 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
         for (uint64_t b = gtid; b < nblocks; b += gsz)
             if (!(it && cm_old[b])) inc[b] = (nbytes - b * 256 >= 256) && (__popc(sigw_g[2 * b]) + __popc(sigw_g[2 * b + 1]) <= 4);
     if (gtid == 0) { st->relax_changed[0] = 0; st->relax_changed[1] = 0; st->iter_changed = 0; st->pad2[0] = 0; }
+    if (gtid < 16 && it == 0) { g_prot_dbg[gtid][0] = ~0ull; g_prot_dbg[gtid][1] = 0; }
     grid_barrier(bar, gridDim.x, epoch);
 
     // (2) phase 0: round 0 evaluates every segment from the canonical state and counts the seams that are not canonical. None: done
@@ -1113,8 +1117,13 @@ prot_iterate(const uint32_t* __restrict__ sigw_g, uint64_t nbytes, uint64_t nblo
     // (4) fixed point reached?
     {
         bool diff = false;
-        for (uint64_t b = gtid; b < nblocks; b += gsz) diff |= __ldcg(&cm_new[b]) != (it ? cm_old[b] : 0);
-        if (diff) atomicOr(&st->iter_changed, 1u);
+        unsigned long long first = ~0ull; unsigned int nd = 0;
+        for (uint64_t b = gtid; b < nblocks; b += gsz)
+            if (__ldcg(&cm_new[b]) != (it ? cm_old[b] : 0)) { diff = true; ++nd; if (b < first) first = b; }
+        if (diff) {
+            atomicOr(&st->iter_changed, 1u);
+            if (it >= 0 && it < 16) { atomicAdd(&g_prot_dbg[it][1], (unsigned long long)nd); atomicMin(&g_prot_dbg[it][0], first); }   // diagnostics
+        }
     }
     grid_barrier(bar, gridDim.x, epoch);
     const bool converged = *((volatile unsigned int*)&st->iter_changed) == 0;
@@ -1533,6 +1542,8 @@ static cudaError_t prot_iterate_coop(int ctas, cudaStream_t stream, const uint32
     void* args[] = {&sigw, &nbytes, &nblocks, &nseg, &st, &it, &inc, &cm_old, &cm_new, &in_state, &out_state, &ptab};
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(prot_iterate), dim3((unsigned)ctas), dim3(PI_THREADS), args, 0, stream);
 }
+
+cudaError_t prot_debug_read(unsigned long long* out32) { return cudaMemcpyFromSymbol(out32, g_prot_dbg, sizeof(unsigned long long) * 32); }
 
 size_t prot_state_bytes(uint64_t nseg_max) { return (2 * (nseg_max + 2) + 64) * sizeof(uint32_t) + prot_table_elems(nseg_max) * sizeof(uint16_t); }
 

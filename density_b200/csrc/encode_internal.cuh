@@ -37,7 +37,8 @@ cudaError_t cham_encode_phase2_stream(const uint8_t* d_in, size_t nbytes, uint8_
 
 // shared pieces of the encoders (chameleon_encode.cu)
 struct Status;
-size_t prot_state_bytes(uint64_t nseg_max);   // segment states + candidate tables of prot_iterate for up to nseg_max segments of 256 blocks
+size_t prot_state_bytes(uint64_t nseg_max);
+cudaError_t prot_debug_read(unsigned long long* out32);   // diagnostics: per fixed-point round {first changed block, changed blocks}   // segment states + candidate tables of prot_iterate for up to nseg_max segments of 256 blocks
 cudaError_t prot_iterate_launch(const uint32_t* sigw_or_null, uint64_t nbytes, uint64_t nblocks, uint32_t nseg, Status* st, int it, uint8_t* inc,
                                 uint8_t* cm_old, uint8_t* cm_new, uint32_t* in_state, uint32_t* out_state, int block_bytes, int num_sms,
                                 cudaStream_t stream);

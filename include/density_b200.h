@@ -198,6 +198,9 @@ DENSITY_B200_API void density_b200_test_set_stage_rounds(int k);
 DENSITY_B200_API void density_b200_test_set_flag_impl(int k);
 /* Same for the Chameleon decode pass (1 = round-1 kernel, 7 = write / verify / mailbox; default 7). */
 DENSITY_B200_API void density_b200_test_set_decode_impl(int k);
+/* Diagnostic: the last copy-map iteration on the current device, per fixed-point round {first block whose copy status changed
+   (~0: none), number of such blocks}: 16 rounds x 2 values. Synchronises the device. */
+DENSITY_B200_API int density_b200_prot_debug(uint64_t* out32);
 /* Library version string. */
 DENSITY_B200_API const char* density_b200_version(void);
 

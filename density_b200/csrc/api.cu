@@ -13,10 +13,13 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace dns {
@@ -48,6 +51,133 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+// ---- pageable host buffers ------------------------------------------------------------------------------------------------------
+// A Rust Vec<u8> (what the reference's callers pass) is pageable memory: cudaMemcpy from / to it goes through the driver's own bounce
+// buffer with one host thread (~8-12 GB/s). The synchronous entry points therefore stage pageable buffers through a pinned ring of
+// two slots per direction with a multi-threaded memcpy, so that the host copy of piece k + 1 overlaps the DMA of piece k.
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool p; return p; }
+    // blocking parallel memcpy
+    void copy(void* dst, const void* src, size_t n) {
+        const size_t nparts = (n >= (8u << 20) && !th_.empty()) ? th_.size() : 1;
+        if (nparts == 1) { memcpy(dst, src, n); return; }
+        Job job; job.left = (int)nparts;
+        const size_t per = ((n + nparts - 1) / nparts + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (size_t k = 0; k < nparts; ++k) {
+                const size_t off = k * per;
+                const size_t len = off >= n ? 0 : (n - off < per ? n - off : per);
+                q_.push_back(Task{static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, len, &job});
+            }
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return job.left == 0; });
+    }
+private:
+    struct Job { int left; };
+    struct Task { uint8_t* d; const uint8_t* s; size_t n; Job* job; };
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned nt = hw >= 128 ? 32 : (hw >= 32 ? 16 : (hw >= 8 ? hw / 2 : 0));
+        for (unsigned i = 0; i < nt; ++i) th_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (stop_ && q_.empty()) return;
+                t = q_.front(); q_.pop_front();
+            }
+            if (t.n) memcpy(t.d, t.s, t.n);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--t.job->left == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::deque<Task> q_;
+    bool stop_ = false;
+};
+
+constexpr size_t PIN_SLOT = 64u << 20;      // bytes per ring slot (= one chunk of the pipelined encode)
+struct PinRing {
+    uint8_t* slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};  // DMA that last used the slot
+    bool used[2] = {false, false};
+    unsigned next = 0;
+    cudaError_t ensure() {
+        for (int k = 0; k < 2; ++k) {
+            if (!slot[k]) { cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&slot[k]), PIN_SLOT, cudaHostAllocDefault); if (e != cudaSuccess) return e; }
+            if (!ev[k]) { cudaError_t e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+        }
+        return cudaSuccess;
+    }
+    void release() {
+        for (int k = 0; k < 2; ++k) { if (slot[k]) cudaFreeHost(slot[k]); if (ev[k]) cudaEventDestroy(ev[k]); slot[k] = nullptr; ev[k] = nullptr; used[k] = false; }
+    }
+};
+
+static bool is_pageable_host(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+// host -> device, asynchronous on `s` for pinned sources; for pageable sources the host copies are done when it returns, the DMA is not
+static cudaError_t h2d_any(PinRing& ring, uint8_t* dst_dev, const uint8_t* src, size_t n, cudaStream_t s, bool pageable) {
+    if (!pageable) return cudaMemcpyAsync(dst_dev, src, n, cudaMemcpyHostToDevice, s);
+    cudaError_t e = ring.ensure();
+    for (size_t off = 0; off < n && e == cudaSuccess; off += PIN_SLOT) {
+        const size_t len = n - off < PIN_SLOT ? n - off : PIN_SLOT;
+        const unsigned k = ring.next++ & 1u;
+        if (ring.used[k]) e = cudaEventSynchronize(ring.ev[k]);
+        if (e != cudaSuccess) break;
+        CopyPool::get().copy(ring.slot[k], src + off, len);
+        e = cudaMemcpyAsync(dst_dev + off, ring.slot[k], len, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaEventRecord(ring.ev[k], s);
+        ring.used[k] = true;
+    }
+    return e;
+}
+// device -> host; synchronous for pageable destinations (returns when the bytes are in `dst`), asynchronous on `s` otherwise
+static cudaError_t d2h_any(PinRing& ring, uint8_t* dst, const uint8_t* src_dev, size_t n, cudaStream_t s, bool pageable) {
+    if (!pageable) return cudaMemcpyAsync(dst, src_dev, n, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = ring.ensure();
+    size_t pend_off = 0, pend_len = 0; unsigned pend_k = 0; bool pending = false;
+    for (size_t off = 0; off < n && e == cudaSuccess; off += PIN_SLOT) {
+        const size_t len = n - off < PIN_SLOT ? n - off : PIN_SLOT;
+        const unsigned k = ring.next++ & 1u;
+        if (ring.used[k] && !(pending && pend_k == k)) e = cudaEventSynchronize(ring.ev[k]);
+        if (e != cudaSuccess) break;
+        e = cudaMemcpyAsync(ring.slot[k], src_dev + off, len, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaEventRecord(ring.ev[k], s);
+        ring.used[k] = true;
+        if (pending && e == cudaSuccess) {       // drain the previous piece while this one is in flight
+            e = cudaEventSynchronize(ring.ev[pend_k]);
+            if (e == cudaSuccess) CopyPool::get().copy(dst + pend_off, ring.slot[pend_k], pend_len);
+        }
+        pend_off = off; pend_len = len; pend_k = k; pending = true;
+    }
+    if (pending && e == cudaSuccess) {
+        e = cudaEventSynchronize(ring.ev[pend_k]);
+        if (e == cudaSuccess) CopyPool::get().copy(dst + pend_off, ring.slot[pend_k], pend_len);
+    }
+    return e;
+}
+
 struct DeviceCtx {
     int dev = -1;
     int num_sms = 0;
@@ -59,6 +189,7 @@ struct DeviceCtx {
     uint32_t chee_epoch = 0;
     uint64_t* h_sizes = nullptr;       // pinned, PIPE_MAX_CHUNKS entries
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    PinRing ring_in, ring_out;         // pinned staging of pageable host buffers
     uint64_t* d_size = nullptr;        // 8 B device
     uint64_t* h_size = nullptr;        // 8 B pinned
     ChamLayout layout{};
@@ -299,16 +430,19 @@ static size_t chameleon_encode_host_pipelined(DeviceCtx* c, const uint8_t* in, s
     uint32_t* d_flag = reinterpret_cast<uint32_t*>(d_sizes + nchunks);
     for (int k = 0; k < 2; ++k) if (!c->ev_h2d[k]) cudaEventCreateWithFlags(&c->ev_h2d[k], cudaEventDisableTiming);
     uint64_t launches = 0;
-    // all H2D copies are queued up front on the copy stream; one event per chunk would be ideal, two rotating events
-    // are enough because the compute stream consumes them in order
+    // pinned input: all H2D copies are queued up front on the copy stream, one event per chunk. Pageable input: chunk 0 is staged
+    // now, chunk i + 1 while the GPU works on chunk i (the host copy into the pinned ring is the slow part)
+    const bool pg_in = is_pageable_host(in), pg_out = is_pageable_host(out);
     std::vector<cudaEvent_t> evs(nchunks, nullptr);
     bool ok = true;
-    for (size_t i = 0; i < nchunks && ok; ++i) {
+    auto stage_chunk = [&](size_t i) {
         const size_t off = i * PIPE_CHUNK, len = (n - off < PIPE_CHUNK) ? (n - off) : PIPE_CHUNK;
-        ok = cudaMemcpyAsync(c->stage_in.p + off, in + off, len, cudaMemcpyHostToDevice, c->h2d_stream) == cudaSuccess;
+        ok = h2d_any(c->ring_in, c->stage_in.p + off, in + off, len, c->h2d_stream, pg_in) == cudaSuccess;
         if (ok) ok = cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming) == cudaSuccess;
         if (ok) ok = cudaEventRecord(evs[i], c->h2d_stream) == cudaSuccess;
-    }
+    };
+    size_t staged = 0;
+    for (; staged < (pg_in ? (size_t)1 : nchunks) && ok; ++staged) stage_chunk(staged);
     size_t out_off = 0;
     bool nonquiet = false;
     e = cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), c->stream);
@@ -324,16 +458,18 @@ static size_t chameleon_encode_host_pipelined(DeviceCtx* c, const uint8_t* in, s
         if (e == cudaSuccess) e = cham_table_fold(d_acc, d_tab, c->stream, &launches);
         if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_sizes + i, d_sizes + i, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_size, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && pg_in && staged < nchunks) { stage_chunk(staged); ++staged; }
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // chunk i done; later H2D copies keep flowing meanwhile
         if (e != cudaSuccess) break;
         if (*reinterpret_cast<uint32_t*>(c->h_size) != 0) { nonquiet = true; break; }
         const uint64_t sz = c->h_sizes[i];
         if (sz == 0) { ok = false; set_error("pipelined encode: device reported an error"); break; }
         if (out_off + sz > out_cap) { ok = false; set_error("output buffer too small"); break; }
-        e = cudaMemcpyAsync(out + out_off, c->stage_out.p + out_off, sz, cudaMemcpyDeviceToHost, c->d2h_stream);
+        e = d2h_any(c->ring_out, out + out_off, c->stage_out.p + out_off, sz, c->d2h_stream, pg_out);
         out_off += sz;
     }
     g_launches += launches;
+    if (nonquiet) for (; staged < nchunks && ok; ++staged) stage_chunk(staged);   // the fallback wants the whole input in stage_in
     cudaError_t e2 = cudaStreamSynchronize(c->h2d_stream);
     cudaError_t e3 = cudaStreamSynchronize(c->d2h_stream);
     for (auto ev : evs) if (ev) cudaEventDestroy(ev);
@@ -372,7 +508,7 @@ static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_
     if (!in_dev && !input_staged) {
         e = c->stage_in.ensure(n + 16);
         if (e != cudaSuccess) { set_error("staging cudaMalloc", e); return 0; }
-        e = cudaMemcpyAsync(c->stage_in.p, in, n, cudaMemcpyHostToDevice, c->stream);
+        e = h2d_any(c->ring_in, c->stage_in.p, in, n, c->stream, is_pageable_host(in));
         if (e != cudaSuccess) { set_error("H2D copy", e); return 0; }
         d_in = c->stage_in.p;
     }
@@ -394,7 +530,7 @@ static size_t run_sync(bool encode, int alg, const uint8_t* in, size_t n, uint8_
     if (produced == 0) { set_error(encode ? "encode failed on device (output capacity?)" : "decode failed on device (malformed stream or output capacity)"); return 0; }
     if (produced > out_cap) { set_error("output buffer too small"); return 0; }
     if (!out_dev) {
-        e = cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, c->stream);
+        e = d2h_any(c->ring_out, out, d_out, produced, c->stream, is_pageable_host(out));
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { set_error("D2H copy", e); return 0; }
     }
@@ -913,6 +1049,7 @@ void density_b200_shutdown(void) {
         if (c.d2h_stream) cudaStreamDestroy(c.d2h_stream);
         if (c.h_sizes) cudaFreeHost(c.h_sizes);
         c.h2d_stream = c.d2h_stream = nullptr; c.h_sizes = nullptr; c.pipe_tables.release();
+        c.ring_in.release(); c.ring_out.release();
         for (auto& set : c.ev) for (auto& e : set) if (e) { cudaEventDestroy(e); e = nullptr; }
         c.d_size = nullptr; c.h_size = nullptr; c.stream = nullptr; c.ready = false;
     }

@@ -437,6 +437,18 @@ def test_chameleon_host_pipelined_path_bit_exact(torch_cuda, codecs, kind):
     assert got.size == want.size and (got == want).all()
 
 
+@pytest.mark.gpu
+def test_chameleon_host_pipelined_path_tiny_last_chunk(torch_cuda, codecs):
+    """The pipelined host path cuts the input into 64 MiB chunks: a 5-byte last chunk (no whole quad) must come out like the
+    oracle's tail, from pageable host buffers (staged through the pinned ring)."""
+    from density_b200 import synth
+    n = 128 * (1 << 20) + 5
+    data = synth.synth_text(n).numpy()
+    want = oracle.encode("chameleon", data)
+    got = gpu_encode(codecs["chameleon"], data)
+    assert got.size == want.size and (got == want).all()
+
+
 @pytest.mark.parametrize("path", [0, 1, 3])
 @pytest.mark.parametrize("nbytes", [5, 263, 264, 300, 4096, 16 * 1024 + 4, 70001, 1 << 20, (1 << 22) + 777, 24 * (1 << 20) + 3])
 def test_chameleon_decode_paths_on_text(torch_cuda, codecs, path, nbytes):

@@ -413,8 +413,12 @@ def run_ours(args):
             del d_k, d_ok
         # config 1: Chameleon round trip on Silesia/dickens through the reference symbols (latency-bound on a GPU; reported, not optimised)
         dk = None
-        for cand, label in ((os.path.join(ROOT, "oracle", "_ref", "dickens.txt"), "benches/data/dickens.txt (10,192,446 B)"),
-                            (os.path.join(ROOT, "tests", "golden", "dickens_200k.bin"), "first 200,000 B of dickens (tests/golden)")):
+        # the file: the reference's convention (benches/utils.rs:6-17): $FILE, else benches/data/dickens.txt (a copy travels in oracle/_ref)
+        cands = [(os.path.join(ROOT, "oracle", "_ref", "dickens.txt"), "benches/data/dickens.txt (10,192,446 B)"),
+                 (os.path.join(ROOT, "tests", "golden", "dickens_200k.bin"), "first 200,000 B of dickens (tests/golden)")]
+        if os.environ.get("FILE"):
+            cands.insert(0, (os.environ["FILE"], "FILE=" + os.environ["FILE"]))
+        for cand, label in cands:
             if os.path.exists(cand):
                 dk, dk_label = np.fromfile(cand, dtype=np.uint8), label
                 break
